@@ -1,0 +1,121 @@
+/* se3b200.h -- C ABI of the B200-native SE(3)-Transformer attention hot path.
+ *
+ * The reference (lucidrains/se3-transformer-pytorch @ e1669ee) has no FFI layer: its boundary is the
+ * Python class SE3Transformer.  This header declares the entry points a native replacement of the hot
+ * path binds at the three tensor-only seams of the reference:
+ *
+ *   neighbour builder inside SE3Transformer.forward   se3_transformer_pytorch.py:1171-1294  -> se3_knn_fwd
+ *   get_basis(r_ij, max_degree)                        basis.py:153-205                      -> se3_basis_fwd
+ *   RadialFunc trunk (net.0 .. net.5)                  se3_transformer_pytorch.py:287-293    -> se3_radial_trunk_fwd
+ *   PairwiseConv + ConvSE3 inner product               se3_transformer_pytorch.py:237-254,
+ *                                                      326-343                               -> se3_tbuild_fwd +
+ *                                                                                               se3_pairwise_{simt,tc}_fwd
+ *   masked_mean pooling of ConvSE3                     utils.py:72-80, S:256-257             -> se3_pool_fwd
+ *   AttentionSE3.forward logits/softmax/aggregate      se3_transformer_pytorch.py:476-517    -> se3_attn_fwd
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous row-major buffer unless marked HOST;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - buffers are borrowed for the duration of the call; the library keeps no state between calls;
+ *   - return value 0 = success; otherwise a negative SE3_E* code and se3_last_error() (HOST string,
+ *     thread-local) describes the failure.  No CPU fallback exists.
+ *   - fp32 arithmetic throughout; the tensor-core kernel evaluates its one dense contraction as a
+ *     3-pass bf16 split (hi*hi + lo*hi + hi*lo, fp32 accumulate), error ~1e-6 relative.
+ */
+#ifndef SE3B200_H
+#define SE3B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE3_OK            0
+#define SE3_EINVAL       -1   /* bad argument / unsupported shape */
+#define SE3_ECUDA        -2   /* CUDA runtime error (launch, attribute) */
+#define SE3_RADIAL_MID   128  /* RadialFunc mid_dim, se3_transformer_pytorch.py:278 */
+#define SE3_TILE_E       128  /* edges per tile (UMMA M) */
+#define SE3_TILE_O        32  /* output channels per tile */
+#define SE3_TILE_IF        4  /* (in-channel, frequency) pairs per tile step */
+
+const char* se3_last_error(void);
+int         se3_abi_version(void);
+
+/* Neighbour graph (S:1171-1294).  For every node i of every cloud: the k smallest "modified" distances over the
+ * other n-1 nodes, ascending (ties: lower node index first), exactly as the reference's remove-self + topk:
+ *   modified = true distance; user neighbor_mask==0 -> FLT_MAX (S:1257); bonded (sparse_adj!=0) -> 0 (S:1262);
+ *   causal and j' >= i on the self-removed grid -> FLT_MAX (S:1266-1268).
+ * out_mask = (modified <= valid_radius) & node_mask[i] & node_mask[j]  (S:1284, 1290-1291).
+ * node_mask, neighbor_mask, sparse_adj may be NULL.  Requires 1 <= k <= n-1 and n-1 <= 4096. */
+int se3_knn_fwd(const float* coors, const uint8_t* node_mask, const uint8_t* neighbor_mask, const uint8_t* sparse_adj,
+                int b, int n, int k, float valid_radius, int causal,
+                int64_t* out_idx, uint8_t* out_mask, float* out_rel_pos, float* out_rel_dist, void* stream);
+
+/* Gather per-pair features onto the neighbour list (batched_index_select at S:1293-1294, utils.py:56-70):
+ * out[b,i,kk,:] = pair_feat[b,i,idx[b,i,kk],:]   with pair_feat [b,n,n,e]. */
+int se3_gather_pairs_fwd(const float* pair_feat, const int64_t* idx, int b, int n, int k, int e, float* out, void* stream);
+
+/* Equivariant basis (basis.py:153-205): real spherical harmonics Y_J, J <= 2*max_degree, evaluated from Cartesian
+ * r_ij without trigonometry, times the constant Q_J tables given as a CSR matrix over R = sum_pairs (2lo+1)(2li+1)f rows
+ * and sum_J (2J+1) columns.  Pair p occupies out[pair_base[p]*E .. ) as [E, rows_p] row-major, rows_p =
+ * pair_row0[p+1]-pair_row0[p]; within a pair row = (p_out*(2li+1)+q_in)*f + f_idx (B:197-198). */
+int se3_basis_fwd(const float* rel_pos, int64_t E, int max_degree,
+                  const int32_t* csr_row_ptr, const int32_t* csr_col, const float* csr_val,
+                  const int32_t* pair_row0, const int32_t* pair_base, int num_pairs,
+                  float* out, void* stream);
+
+/* Radial trunk (S:287-293) for `num_pairs` independent RadialFunc MLPs over the same edge features:
+ * g = GELU(LN(W2 GELU(LN(W1 feat + b1)) + b2)), exact erf GELU, LN eps 1e-5.
+ * params: per pair, contiguous floats [W1^T (in_dim x 128) | b1 | ln1_w | ln1_b | W2^T (128 x 128) | b2 | ln2_w | ln2_b].
+ * out_g   : [num_pairs, E, 128] fp32 (may be NULL)
+ * out_img : bf16 hi/lo UMMA operand images, [num_pairs, ceil(E/128)] tiles of 64 KiB (may be NULL); see DESIGN.md. */
+int se3_radial_trunk_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params,
+                         float* out_g, void* out_img, void* stream);
+
+/* T[e,i,f,p] = sum_q basis[e,p,q,f] * x[b, idx[e], i, q]   (the gather at S:237 fused with the basis contraction of
+ * the factored form).  x: [b,n,Ci,Q], basis_pair: [E,P,Q,F], E = b*n*k.  Edge tiles
+ * [tile_begin, tile_begin+tile_count) (128 edges each) are written to T in tile layout
+ * [tile_count][ceil(Ci*F/4)][4][ceil(P/4)][128][4] floats (zero padded), so a ConvSE3 can be evaluated in edge chunks
+ * (the B200 counterpart of the reference's node-axis `splits`, S:243-252). */
+int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* basis_pair, int b, int n, int k,
+                   int Ci, int P, int Q, int F, int64_t tile_begin, int64_t tile_count, float* T, void* stream);
+
+/* out[e,o,p] (+)= sum_{i,f} (W3[(o*Ci+i)*F+f,:].g[e,:] + b3[(o*Ci+i)*F+f]) * T[e,i,f,p]     (S:299, 336-343, 251-254)
+ * fp32 SIMT version, any shape.  g: [E,128]; W3: [Co*Ci*F,128]; out: [E,Co,P]. */
+int se3_pairwise_simt_fwd(const float* g, const float* W3, const float* b3, const float* T,
+                          int64_t E, int Co, int Ci, int F, int P, int accumulate, float* out, void* stream);
+
+/* Pack RadialFunc.net.6 weight/bias into the tensor-core operand image (once per weight update).
+ * bytes needed: se3_w3_image_bytes(Co, Ci, F).  Requires Co % 32 == 0. */
+int64_t se3_w3_image_bytes(int Co, int Ci, int F);
+int se3_pack_w3(const float* W3, const float* b3, int Co, int Ci, int F, void* image, void* stream);
+
+/* Same contraction as se3_pairwise_simt_fwd on the tcgen05 tensor cores (sm_100a only): g_img from
+ * se3_radial_trunk_fwd (one pair's slice), w_img from se3_pack_w3, T from se3_tbuild_fwd. */
+int se3_pairwise_tc_fwd(const void* g_img, const void* w_img, const float* T,
+                        int64_t E, int Co, int Ci, int F, int P, int accumulate, float* out, void* stream);
+/* Diagnostic for tests: as above, and dumps (R + bias) of the first (i,f) step as [ceil(E/128), Co/32, 128, 128] fp32
+ * (column = if_local*32 + o_local). */
+int se3_pairwise_tc_debug(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+                          int P, int accumulate, float* out, float* dumpR, void* stream);
+
+/* Masked mean over the neighbour axis (utils.py:72-80): x [B, K, C] , mask [B, K] (NULL = plain mean) -> out [B, C]. */
+int se3_pool_fwd(const float* x, const uint8_t* mask, int64_t B, int K, int64_t C, float* out, void* stream);
+
+/* Attention for one degree (S:476-517): for every node i and head h
+ *   keys/values along j = [global (G) | null (0/1) | self (0/1) | K neighbours]  (prepend order of S:485,499,505)
+ *   sim_j = scale * sum_{d,m} q[b,i,h,d,m] k_j[d,m];  masked neighbour -> -FLT_MAX (S:510-513); softmax over j; out = sum_j a_j v_j.
+ * q, out: [b,n,H*Dh,M].  k, v: [b,n,K,Ckv,M] with Ckv = kv_heads*Dh, kv_heads in {H,1} (1 = OneHeadedKVAttentionSE3, S:643-651).
+ * If k_idx != NULL, k is node level [b,n,Ckv,M] and neighbour j reads k[b, k_idx[b,i,j]] (linear_proj_keys, S:461-463).
+ * self_k/self_v: [b,n,Ckv,M] or NULL; null_k/null_v: [Ckv,M] or NULL; global_k/global_v: [b,G,Ckv,M] or NULL.
+ * nmask: [b,n,K] or NULL. */
+int se3_attn_fwd(const float* q, const float* k, const float* v, const int64_t* k_idx,
+                 const float* self_k, const float* self_v, const float* null_k, const float* null_v,
+                 const float* global_k, const float* global_v, int G, const uint8_t* nmask,
+                 int b, int n, int K, int H, int Dh, int M, int kv_heads, float scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3B200_H */

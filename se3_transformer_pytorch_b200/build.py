@@ -1,0 +1,80 @@
+"""In-tree build of libse3b200.so (hand-written sm_100a kernels + C ABI) with nvcc.
+
+No torch extension machinery: the library exposes a plain C ABI (include/se3b200.h) and is loaded with ctypes.
+nvcc cross-compiles for sm_100a without a GPU, so this runs in the CPU-only dev container too.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, 'csrc')
+LIB = os.path.join(PKG, 'libse3b200.so')
+STAMP = os.path.join(PKG, '.libse3b200.stamp')
+SOURCES = ['api.cu', 'graph.cu', 'basis.cu', 'radial.cu', 'tbuild.cu', 'pairwise_simt.cu', 'pairwise_tc.cu', 'attention.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found (needed to build libse3b200.so)')
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(os.path.dirname(PKG), 'include', 'se3b200.h')]
+    for f in files:
+        with open(f, 'rb') as fh:
+            h.update(f.encode() + b'\0' + fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current():
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == _digest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into one shared library next to this file."""
+    if not force and is_current():
+        return LIB
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
+    objs = []
+    procs = []
+    objdir = os.path.join(PKG, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        cmd = [nvcc, *flags, '-c', os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+            print(' '.join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(out, file=sys.stderr)
+        if p.returncode != 0:
+            failed = True
+            print(f'nvcc failed on {src}', file=sys.stderr)
+    if failed:
+        raise RuntimeError('libse3b200 build failed')
+    subprocess.check_call([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB, *objs])
+    with open(STAMP, 'w') as f:
+        f.write(_digest())
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

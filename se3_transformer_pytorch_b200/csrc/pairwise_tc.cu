@@ -1,0 +1,433 @@
+// K4 (tensor cores): the fused pairwise kernel for one (degree_in, degree_out) pair of one ConvSE3.
+//
+//   out[e,o,p] (+)= sum_{i,f} ( W3[(o*Ci+i)*F+f,:] . g[e,:] + b3 ) * T[e,i,f,p]
+//
+// = RadialFunc.net.6 (se3_transformer_pytorch.py:294,299) + PairwiseConv.forward (S:326-343) + the per-edge
+// mat-vec and sum over degree_in of ConvSE3.forward (S:251-254), in the factored form of SURVEY.md A.4.
+//
+// The only dense contraction, R = g . W3^T  (M = 128 edges, N = 128 (o,i,f) columns, K = 128), runs on the 5th-gen
+// tensor cores (tcgen05.mma, cta_group::1, M128 N128 K16, bf16 x bf16 -> fp32 in TMEM).  fp32 parity is kept with a
+// 3-pass bf16 split:  g = g_hi + g_lo, W = W_hi + W_lo,  R ~= g_hi W_hi + g_lo W_hi + g_hi W_lo  (24 MMAs per tile).
+// R never leaves the SM: epilogue warps read the accumulator tile with tcgen05.ld, add the bias and contract it with the
+// per-edge T block (packed fp32x2 FMAs), keeping out[e, 32 o, P] in registers across the whole (i,f) loop.
+//
+// One CTA = (tile of 128 edges) x (block of 32 output channels); it loops over ceil(Ci*F/4) steps.  Per step the
+// column order is n = if_local*32 + o_local.  All operands are pre-imaged in global memory in exactly the layout the
+// kernel wants in shared memory (128-byte-swizzled K-major UMMA tiles; T in [if][p-quad][edge][4]) so every stage is
+// filled by 1-D TMA bulk copies (cp.async.bulk, completion on mbarriers) with no tensor maps.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (warps 2,3 idle; the warpgroup
+// gives its registers away with setmaxnreg), warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking
+// 16 of the 32 output channels, 208 registers each).
+// Pipelines: W stages (producer -> MMA, released by tcgen05.commit), T/bias stages (producer -> epilogue),
+// TMEM accumulator double buffer (MMA -> epilogue).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace se3 {
+
+constexpr int kTcThreads = 384;                // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
+constexpr uint32_t kImgBytes = 65536;            // one 128x128 hi+lo operand image (4 sub-tiles of 16 KiB)
+constexpr uint32_t kSubBytes = 16384;            // 128 rows x 64 bf16, SW128
+constexpr uint32_t kBiasBytes = 512;             // 128 fp32
+constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
+constexpr uint32_t kTmemCols = 256;              // 2 accumulator buffers x 128 columns
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset = 1024 B  [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+  const int kh = k >> 6, kk = k & 63;
+  const int chunk = (kk >> 3) ^ (r & 7);
+  return (uint32_t)(kh * kSubBytes + r * 128 + chunk * 16 + (kk & 7) * 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight image packer: W3 fp32 [Co*Ci*F, 128] -> per (o-block, if-block) tile: [hi k0|hi k1|lo k0|lo k1|bias fp32 x128]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __restrict__ b3, int Co, int CiF, int NIFB,
+                               uint8_t* __restrict__ img) {
+  const int64_t tile = blockIdx.x;                 // ob * NIFB + ifb
+  const int ob = (int)(tile / NIFB), ifb = (int)(tile % NIFB);
+  uint8_t* dst = img + (size_t)tile * kWTileBytes;
+  for (int t = threadIdx.x; t < 128 * 128; t += blockDim.x) {
+    const int r = t >> 7, k = t & 127;
+    const int o = ob * SE3_TILE_O + (r & 31), ifx = ifb * SE3_TILE_IF + (r >> 5);
+    const float w = (ifx < CiF) ? W3[((size_t)o * CiF + ifx) * SE3_RADIAL_MID + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const uint32_t off = sw128_off(r, k);
+    *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kSubBytes + off) = lo;
+    if (k == 0) reinterpret_cast<float*>(dst + kImgBytes)[r] = (ifx < CiF) ? b3[(size_t)o * CiF + ifx] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------------------
+struct TcSmem {                                   // offsets from the 1024-aligned base
+  static constexpr uint32_t A = 0;
+  static constexpr uint32_t W0 = kImgBytes;
+  static constexpr uint32_t T0 = 3 * kImgBytes;
+};
+
+template <int P, bool kDumpR>
+__global__ void __launch_bounds__(kTcThreads, 1)
+pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict__ w_img, const float* __restrict__ T,
+                   int64_t E, int Co, int NIFB, int accumulate, float* __restrict__ out, float* __restrict__ dumpR) {
+  constexpr int PH = (P + 3) / 4;
+  constexpr uint32_t kTBytes = PH * 8192u;         // 4 (i,f) x PH x 128 edges x 16 B
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sA = base + TcSmem::A;
+  const uint32_t sW = base + TcSmem::W0;           // + st * kImgBytes
+  const uint32_t sT = base + TcSmem::T0;           // + st * kTBytes
+  const uint32_t sBias = sT + 2 * kTBytes;         // + st * kBiasBytes
+  const uint32_t sBar = sBias + 2 * kBiasBytes;    // 8-byte barriers
+  // barrier ids
+  const uint32_t bar_a_full = sBar + 0;
+  const uint32_t bar_w_full = sBar + 8;            // [2]
+  const uint32_t bar_w_empty = sBar + 24;          // [2]
+  const uint32_t bar_t_full = sBar + 40;           // [2]
+  const uint32_t bar_t_empty = sBar + 56;          // [2]
+  const uint32_t bar_tm_full = sBar + 72;          // [2]
+  const uint32_t bar_tm_empty = sBar + 88;         // [2]
+  const uint32_t s_tmem_slot = sBar + 104;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t mt = blockIdx.x;
+  const int ob = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, 1);
+      mbar_init(bar_t_full + 8 * s, 1);
+      mbar_init(bar_t_empty + 8 * s, 8);
+      mbar_init(bar_tm_full + 8 * s, 1);
+      mbar_init(bar_tm_empty + 8 * s, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_a_full, kImgBytes);
+      bulk_g2s(sA, g_img + (size_t)mt * kImgBytes, kImgBytes, bar_a_full);
+      const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kWTileBytes;
+      const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
+      for (int s = 0; s < NIFB; ++s) {
+        const int st = s & 1;
+        const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+        mbar_wait(bar_w_empty + 8 * st, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_w_full + 8 * st, kImgBytes);
+        bulk_g2s(sW + st * kImgBytes, wsrc + (size_t)s * kWTileBytes, kImgBytes, bar_w_full + 8 * st);
+        mbar_wait(bar_t_empty + 8 * st, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_t_full + 8 * st, kTBytes + kBiasBytes);
+        bulk_g2s(sT + st * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * st);
+        bulk_g2s(sBias + st * kBiasBytes, wsrc + (size_t)s * kWTileBytes + kImgBytes, kBiasBytes, bar_t_full + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(bar_a_full, 0);
+      for (int s = 0; s < NIFB; ++s) {
+        const int st = s & 1;
+        const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+        mbar_wait(bar_w_full + 8 * st, ph);
+        mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
+        const uint32_t wbase = sW + st * kImgBytes;
+        uint32_t accum = 0;
+        // pass 0: g_hi x W_hi   pass 1: g_lo x W_hi   pass 2: g_hi x W_lo
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_part = (pass == 1) ? 2u * kSubBytes : 0u;
+          const uint32_t b_part = (pass == 2) ? 2u * kSubBytes : 0u;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint64_t ad = umma_desc_sw128(sA + a_part + kh * kSubBytes + k16 * 32);
+              const uint64_t bd = umma_desc_sw128(wbase + b_part + kh * kSubBytes + k16 * 32);
+              tc_mma_bf16(d_tmem, ad, bd, kIdesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        tc_commit(bar_w_empty + 8 * st);      // W stage free once these MMAs retire
+        tc_commit(bar_tm_full + 8 * st);      // accumulator ready for the epilogue
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;          // which 16 of the 32 output channels
+    const int el = q * 32 + lane;              // edge row inside the tile
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    unsigned long long acc[8][P];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[a][p] = 0ull;
+
+    for (int s = 0; s < NIFB; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+      mbar_wait(bar_t_full + 8 * st, ph);
+      mbar_wait(bar_tm_full + 8 * st, ph);
+      tc_fence_after();
+      const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + st * kTBytes);
+      const float4* Bs = reinterpret_cast<const float4*>(base_ptr + (sBias - base) + st * kBiasBytes);
+      const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + half * 16);
+#pragma unroll
+      for (int pair = 0; pair < 2; ++pair) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tcol + (uint32_t)((2 * pair) * 32), r0);
+        tmem_ld16(tcol + (uint32_t)((2 * pair + 1) * 32), r1);
+        tmem_ld_wait();
+        if (pair == 1) {
+          // every tcgen05.ld of this step has completed: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
+        }
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int ifl = 2 * pair + sub;
+          const uint32_t(&r)[16] = sub == 0 ? r0 : r1;
+          float tv[PH * 4];
+#pragma unroll
+          for (int h4 = 0; h4 < PH; ++h4) {
+            const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
+            tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
+          }
+          unsigned long long t2[P];
+#pragma unroll
+          for (int p = 0; p < P; ++p) t2[p] = pack2(tv[p], tv[p]);
+#pragma unroll
+          for (int b4 = 0; b4 < 4; ++b4) {
+            const float4 bb = Bs[(ifl * 32 + half * 16) / 4 + b4];
+            const unsigned long long R0 = add2(pack2(__uint_as_float(r[b4 * 4 + 0]), __uint_as_float(r[b4 * 4 + 1])), pack2(bb.x, bb.y));
+            const unsigned long long R1 = add2(pack2(__uint_as_float(r[b4 * 4 + 2]), __uint_as_float(r[b4 * 4 + 3])), pack2(bb.z, bb.w));
+            if (kDumpR && s == 0) {
+              float a0, a1, a2, a3;
+              unpack2(R0, a0, a1);
+              unpack2(R1, a2, a3);
+              float* dr = dumpR + (((size_t)mt * gridDim.y + ob) * 128 + el) * 128 + ifl * 32 + half * 16 + b4 * 4;
+              dr[0] = a0; dr[1] = a1; dr[2] = a2; dr[3] = a3;
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              acc[b4 * 2 + 0][p] = fma2(R0, t2[p], acc[b4 * 2 + 0][p]);
+              acc[b4 * 2 + 1][p] = fma2(R1, t2[p], acc[b4 * 2 + 1][p]);
+            }
+          }
+        }
+        if (pair == 1) {
+          // T / bias stage fully consumed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty + 8 * st);
+        }
+      }
+    }
+    // write out[e, ob*32 + half*16 + (0..15), 0..P)
+    const int64_t e = mt * SE3_TILE_E + el;
+    if (e < E) {
+      float* dst = out + ((size_t)e * Co + (size_t)ob * SE3_TILE_O + half * 16) * P;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          float v0, v1;
+          unpack2(acc[a][p], v0, v1);
+          float* d0 = dst + (2 * a) * P + p;
+          float* d1 = dst + (2 * a + 1) * P + p;
+          if (accumulate) { v0 += *d0; v1 += *d1; }
+          *d0 = v0;
+          *d1 = v1;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int P>
+static size_t tc_smem_bytes() {
+  constexpr int PH = (P + 3) / 4;
+  return 1024 + 3 * kImgBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 128;
+}
+
+template <int P, bool kDumpR>
+static int launch_tc(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int NIFB, int accumulate,
+                     float* out, float* dumpR, cudaStream_t s) {
+  const size_t smem = tc_smem_bytes<P>();
+  auto kern = pairwise_tc_kernel<P, kDumpR>;
+  SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(E, SE3_TILE_E), (unsigned)(Co / SE3_TILE_O));
+  kern<<<grid, kTcThreads, smem, s>>>(reinterpret_cast<const uint8_t*>(g_img), reinterpret_cast<const uint8_t*>(w_img), T, E, Co,
+                                      NIFB, accumulate, out, dumpR);
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+template <bool kDumpR>
+static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                       int accumulate, float* out, float* dumpR, void* stream) {
+  SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_tc_fwd: bad sizes");
+  SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_tc_fwd: Co=%d must be a multiple of %d (use the SIMT kernel)", Co, SE3_TILE_O);
+  SE3_REQUIRE(P == 1 || P == 3 || P == 5 || P == 7, "se3_pairwise_tc_fwd: P=%d unsupported (degree_out <= 3)", P);
+  SE3_REQUIRE(ceil_div(E, SE3_TILE_E) < 2147483647ll && Co / SE3_TILE_O <= 65535, "se3_pairwise_tc_fwd: grid too large");
+  const int NIFB = (int)ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  cudaStream_t s = as_stream(stream);
+  switch (P) {
+    case 1: return launch_tc<1, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
+    case 3: return launch_tc<3, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
+    case 5: return launch_tc<5, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
+    default: return launch_tc<7, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
+  }
+}
+
+}  // namespace se3
+
+extern "C" int64_t se3_w3_image_bytes(int Co, int Ci, int F) {
+  if (Co <= 0 || Ci <= 0 || F <= 0 || Co % SE3_TILE_O != 0) return -1;
+  const int64_t NIFB = se3::ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  return (int64_t)(Co / SE3_TILE_O) * NIFB * se3::kWTileBytes;
+}
+
+extern "C" int se3_pack_w3(const float* W3, const float* b3, int Co, int Ci, int F, void* image, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(Co > 0 && Ci > 0 && F > 0 && Co % SE3_TILE_O == 0, "se3_pack_w3: Co must be a positive multiple of %d", SE3_TILE_O);
+  const int CiF = Ci * F;
+  const int NIFB = (int)ceil_div(CiF, SE3_TILE_IF);
+  const int64_t tiles = (int64_t)(Co / SE3_TILE_O) * NIFB;
+  SE3_REQUIRE(tiles < 2147483647ll, "se3_pack_w3: too many tiles");
+  pack_w3_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(W3, b3, Co, CiF, NIFB, reinterpret_cast<uint8_t*>(image));
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+extern "C" int se3_pairwise_tc_fwd(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+                                   int P, int accumulate, float* out, void* stream) {
+  return se3::dispatch_tc<false>(g_img, w_img, T, E, Co, Ci, F, P, accumulate, out, nullptr, stream);
+}
+
+// Diagnostic (tests only): same kernel, additionally dumps R + bias of step 0 as [edge tiles, Co/32, 128 edges, 128 cols].
+extern "C" int se3_pairwise_tc_debug(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+                                     int P, int accumulate, float* out, float* dumpR, void* stream) {
+  return se3::dispatch_tc<true>(g_img, w_img, T, E, Co, Ci, F, P, accumulate, out, dumpR, stream);
+}

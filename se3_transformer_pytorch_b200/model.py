@@ -1,0 +1,648 @@
+"""Host-side mirror of the reference's module tree for the SE(3) attention hot path.
+
+Same constructor, forward signature, assertions and state_dict key/shape layout as
+lucidrains/se3-transformer-pytorch v0.9.0 (se3_transformer_pytorch.py:936-1375), so
+`ours.load_state_dict(reference.state_dict())` works.  The hot path -- neighbour graph, spherical-harmonic / CG basis,
+radial trunk, pairwise tensor product (tcgen05), pooling, attention -- runs in the hand-written sm_100a kernels of
+libse3b200.so through `ops`; the cheap glue around it (embeddings, LinearSE3 GEMMs, NormSE3, residuals) stays torch.
+
+Forward only: everything runs under torch.no_grad().  CUDA only: there is no CPU fallback.
+"""
+from math import sqrt
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+def exists(v):
+    return v is not None
+
+
+def default(v, d):
+    return v if exists(v) else d
+
+
+def to_order(degree):
+    return 2 * degree + 1
+
+
+class Fiber:
+    """Ordered list of (degree, channels) (reference S:20-59)."""
+
+    def __init__(self, structure):
+        if isinstance(structure, dict):
+            structure = list(structure.items())
+        self.structure = [(int(d), int(c)) for d, c in structure]
+
+    @staticmethod
+    def create(num_degrees, dim):
+        dims = dim if isinstance(dim, tuple) else (dim,) * num_degrees
+        return Fiber([(d, c) for d, c in zip(range(num_degrees), dims)])
+
+    @property
+    def degrees(self):
+        return [d for d, _ in self.structure]
+
+    @property
+    def dims(self):
+        return list(dict.fromkeys(c for _, c in self.structure))
+
+    def __getitem__(self, degree):
+        return dict(self.structure)[degree]
+
+    def __iter__(self):
+        return iter(self.structure)
+
+    def shared(self, other):
+        """(degree, dim_self, dim_other) for degrees present in both (reference S:52-59)."""
+        od = dict(other.structure)
+        return [(d, c, od[d]) for d, c in self.structure if d in od]
+
+
+def residual_add(x, res):
+    return {d: (t + res[d] if d in res else t) for d, t in x.items()}
+
+
+class LinearSE3(nn.Module):
+    """Per-degree channel mix (reference S:78-95): a plain GEMM, left to cuBLAS."""
+
+    def __init__(self, fiber_in, fiber_out):
+        super().__init__()
+        self.weights = nn.ParameterDict()
+        for degree, dim_in, dim_out in fiber_in.shared(fiber_out):
+            self.weights[str(degree)] = nn.Parameter(torch.randn(dim_in, dim_out) / sqrt(dim_in))
+
+    def forward(self, x):
+        out = {}
+        for degree, w in self.weights.items():
+            t = x[degree]                                            # [b, n, d, m]
+            out[degree] = torch.matmul(t.transpose(-1, -2), w).transpose(-1, -2).contiguous()
+        return out
+
+
+class NormSE3(nn.Module):
+    """Norm nonlinearity (reference S:97-152)."""
+
+    def __init__(self, fiber, nonlin=None, gated_scale=False, eps=1e-12):
+        super().__init__()
+        self.fiber = fiber
+        self.nonlin = nonlin if nonlin is not None else nn.GELU()
+        self.eps = eps
+        self.transform = nn.ModuleDict()
+        for degree, chan in fiber:
+            pd = nn.ParameterDict()
+            if gated_scale:
+                pd['w_gate'] = nn.Parameter(torch.empty(chan, chan).uniform_(-1e-3, 1e-3))
+            else:
+                pd['scale'] = nn.Parameter(torch.ones(1, 1, chan))
+            self.transform[str(degree)] = pd
+
+    def forward(self, features):
+        out = {}
+        for degree, t in features.items():
+            norm = t.norm(dim=-1, keepdim=True).clamp(min=self.eps)
+            phase = t / norm
+            pd = self.transform[degree]
+            tr = norm.squeeze(-1)
+            scale = pd['scale'] if 'scale' in pd else torch.matmul(tr, pd['w_gate'])
+            tr = self.nonlin(tr * scale)
+            out[degree] = (tr.unsqueeze(-1) * phase).view(*t.shape)
+        return out
+
+
+class RadialFunc(nn.Module):
+    """Parameter holder for the radial MLP (reference S:270-299).  `net` keeps the reference's Sequential indices
+    (0 Linear, 1 LayerNorm, 3 Linear, 4 LayerNorm, 6 Linear) so state_dict keys match; evaluation happens in the
+    fused kernels, never here."""
+
+    def __init__(self, num_freq, in_dim, out_dim, edge_dim=0, mid_dim=ops.RADIAL_MID):
+        super().__init__()
+        assert mid_dim == ops.RADIAL_MID
+        self.num_freq, self.in_dim, self.out_dim, self.edge_dim = num_freq, in_dim, out_dim, edge_dim
+        self.net = nn.ModuleDict({
+            '0': nn.Linear(edge_dim + 1, mid_dim),
+            '1': nn.LayerNorm(mid_dim),
+            '3': nn.Linear(mid_dim, mid_dim),
+            '4': nn.LayerNorm(mid_dim),
+            '6': nn.Linear(mid_dim, num_freq * in_dim * out_dim),
+        })
+
+    def trunk_params(self):
+        n = self.net
+        return torch.cat([n['0'].weight.t().reshape(-1), n['0'].bias, n['1'].weight, n['1'].bias,
+                          n['3'].weight.t().reshape(-1), n['3'].bias, n['4'].weight, n['4'].bias])
+
+
+class PairwiseConv(nn.Module):
+    """Holder for one (degree_in, degree_out) radial profile (reference S:301-343)."""
+
+    def __init__(self, degree_in, nc_in, degree_out, nc_out, edge_dim=0):
+        super().__init__()
+        self.degree_in, self.degree_out, self.nc_in, self.nc_out = degree_in, degree_out, nc_in, nc_out
+        self.num_freq = to_order(min(degree_in, degree_out))
+        self.d_out = to_order(degree_out)
+        self.rp = RadialFunc(self.num_freq, nc_in, nc_out, edge_dim)
+
+
+# upper bound on the T workspace (bytes); larger convolutions are evaluated in edge chunks
+T_WORKSPACE_BYTES = int(8 * 2 ** 30)
+
+
+class ConvSE3(nn.Module):
+    """Tensor-field-network layer (reference S:154-268) on the fused kernels."""
+
+    def __init__(self, fiber_in, fiber_out, self_interaction=True, pool=True, edge_dim=0, fourier_encode_dist=False,
+                 num_fourier_features=4, splits=4):
+        super().__init__()
+        self.fiber_in, self.fiber_out = fiber_in, fiber_out
+        self.edge_dim = edge_dim
+        self.self_interaction = self_interaction
+        self.num_fourier_features = num_fourier_features
+        self.fourier_encode_dist = fourier_encode_dist
+        self.splits = splits          # accepted for API parity; chunking is by T_WORKSPACE_BYTES instead
+        edge_dim += 0 if not fourier_encode_dist else num_fourier_features * 2
+        self.in_dim = edge_dim + 1
+        self.kernel_unary = nn.ModuleDict()
+        self.pairs = []
+        for di, mi in fiber_in:
+            for do, mo in fiber_out:
+                self.kernel_unary[f'({di},{do})'] = PairwiseConv(di, mi, do, mo, edge_dim=edge_dim)
+                self.pairs.append((di, do))
+        self.pool = pool
+        if self_interaction:
+            assert self.pool, 'must pool edges if followed with self interaction'
+            self.self_interact = LinearSE3(fiber_in, fiber_out)
+        self._packed = None
+        self.free_master = False
+
+    # ---- packed weights ---------------------------------------------------------------------------------
+    def _param_version(self):
+        v = []
+        for p in self.kernel_unary.parameters():
+            v.append((p._version, p.data_ptr()))
+        return tuple(v)
+
+    def packed(self):
+        """Trunk parameter pack [pairs, stride] + tensor-core images of net.6 (built lazily, rebuilt when weights change)."""
+        ver = None if self.free_master else self._param_version()
+        if self._packed is not None and (self.free_master or self._packed['version'] == ver):
+            return self._packed
+        with torch.no_grad():
+            trunk = torch.stack([self.kernel_unary[f'({di},{do})'].rp.trunk_params() for di, do in self.pairs]).contiguous()
+            dev = trunk.device
+            images = {}
+            for di, do in self.pairs:
+                pc = self.kernel_unary[f'({di},{do})']
+                if ops.tc_supported(dev, pc.nc_out, pc.d_out):
+                    lin = pc.rp.net['6']
+                    images[(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
+        self._packed = dict(version=ver, trunk=trunk, images=images)
+        return self._packed
+
+    def pack_weights(self, free_master=False):
+        """Build the packed weights now; with free_master=True the fp32 net.6 weights of tensor-core pairs are
+        released (inference-only: state_dict() no longer holds them)."""
+        pk = self.packed()
+        if free_master:
+            self.free_master = True
+            for key, img in pk['images'].items():
+                lin = self.kernel_unary[f'({key[0]},{key[1]})'].rp.net['6']
+                lin.weight.data = torch.empty(0, device=img.device)
+        return pk
+
+    # ---- forward ----------------------------------------------------------------------------------------
+    def edge_features(self, edge_info, rel_dist):
+        _, _, edges = edge_info
+        rd = rel_dist.unsqueeze(-1)
+        if self.fourier_encode_dist:
+            # reference utils.py:96-104: [sin(x / 2^s), cos(x / 2^s), x]
+            scales = 2 ** torch.arange(self.num_fourier_features, device=rd.device, dtype=rd.dtype)
+            xs = rd / scales
+            rd = torch.cat([xs.sin(), xs.cos(), rd], dim=-1)
+        feat = torch.cat((rd, edges), dim=-1) if exists(edges) else rd
+        return feat.reshape(-1, feat.shape[-1]).contiguous()
+
+    def forward(self, inp, edge_info, rel_dist=None, basis=None):
+        return conv_forward([self], inp, edge_info, rel_dist, basis)[0]
+
+
+def conv_forward(convs, inp, edge_info, rel_dist, basis):
+    """Evaluate one or more ConvSE3 that share input features, graph and fibers (to_k / to_v of an attention block)
+    in a single sweep: the T blocks (gather x basis) are built once per (degree pair, edge chunk) and consumed by every
+    convolution's fused pairwise kernel."""
+    c0 = convs[0]
+    idx, nmask, _ = edge_info
+    b, n, k = idx.shape
+    E = b * n * k
+    dev = idx.device
+    flat, plan = basis                       # BasisFlat
+    bpairs = ops.basis_pairs(flat, plan, E)
+    n_tiles = (E + ops.TILE_E - 1) // ops.TILE_E
+
+    states = []
+    for conv in convs:
+        assert conv.pairs == c0.pairs and conv.in_dim == c0.in_dim
+        pk = conv.packed()
+        feat = conv.edge_features(edge_info, rel_dist)
+        assert feat.shape[-1] == conv.in_dim, f'edge feature width {feat.shape[-1]} != {conv.in_dim}'
+        use_tc = {p: (p in pk['images']) for p in conv.pairs}
+        any_tc, any_simt = any(use_tc.values()), not all(use_tc.values())
+        g, img = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs), want_g=any_simt, want_img=any_tc)
+        outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
+        states.append(dict(conv=conv, pk=pk, g=g, img=img, outs=outs, use_tc=use_tc))
+
+    # chunk over edge tiles so that the largest T block fits the workspace
+    worst = max(ops.t_numel(1, mi, to_order(min(di, do)), to_order(do)) * 4
+                for di, mi in c0.fiber_in for do, _ in c0.fiber_out)
+    tiles_per_chunk = max(1, min(n_tiles, T_WORKSPACE_BYTES // worst))
+    workspace = None
+    for t0 in range(0, n_tiles, tiles_per_chunk):
+        tc = min(tiles_per_chunk, n_tiles - t0)
+        e0 = t0 * ops.TILE_E
+        ec = min(E - e0, tc * ops.TILE_E)
+        for do, mo in c0.fiber_out:
+            P = to_order(do)
+            first = True
+            for di, mi in c0.fiber_in:
+                Fq = to_order(min(di, do))
+                workspace = ops.tbuild(inp[str(di)], idx, bpairs[(di, do)], di, do, t0, tc, out=workspace)
+                pi = c0.pairs.index((di, do))
+                for st in states:
+                    conv = st['conv']
+                    out = st['outs'][do][e0:e0 + ec]
+                    if st['use_tc'][(di, do)]:
+                        ops.pairwise_tc(st['img'][pi, t0:t0 + tc], st['pk']['images'][(di, do)], workspace, ec, mo, mi, Fq, P,
+                                        out, accumulate=not first)
+                    else:
+                        lin = conv.kernel_unary[f'({di},{do})'].rp.net['6']
+                        ops.pairwise_simt(st['g'][pi, e0:e0 + ec], lin.weight, lin.bias, workspace, ec, mo, mi, Fq, P, out,
+                                          accumulate=not first)
+                first = False
+
+    results = []
+    for st in states:
+        conv = st['conv']
+        outputs = {}
+        for do, mo in conv.fiber_out:
+            o = st['outs'][do].view(b, n, k, mo, to_order(do))
+            if conv.pool:
+                o = ops.pool(o, nmask)
+            outputs[str(do)] = o
+        if conv.self_interaction:
+            outputs = residual_add(outputs, conv.self_interact(inp))
+        results.append(outputs)
+    return results
+
+
+class FeedForwardSE3(nn.Module):
+    """reference S:347-365"""
+
+    def __init__(self, fiber, mult=4):
+        super().__init__()
+        hidden = Fiber([(d, c * mult) for d, c in fiber])
+        self.project_in = LinearSE3(fiber, hidden)
+        self.nonlin = NormSE3(hidden)
+        self.project_out = LinearSE3(hidden, fiber)
+
+    def forward(self, x):
+        return self.project_out(self.nonlin(self.project_in(x)))
+
+
+class FeedForwardBlockSE3(nn.Module):
+    """reference S:367-383"""
+
+    def __init__(self, fiber, norm_gated_scale=False):
+        super().__init__()
+        self.prenorm = NormSE3(fiber, gated_scale=norm_gated_scale)
+        self.feedforward = FeedForwardSE3(fiber)
+
+    def forward(self, x):
+        return residual_add(self.feedforward(self.prenorm(x)), x)
+
+
+class AttentionSE3(nn.Module):
+    """AttentionSE3 (reference S:387-519) and, with one_headed=True, OneHeadedKVAttentionSE3 (S:522-654)."""
+
+    def __init__(self, fiber, dim_head=64, heads=8, attend_self=False, edge_dim=None, fourier_encode_dist=False,
+                 rel_dist_num_fourier_features=4, use_null_kv=False, splits=4, global_feats_dim=None, linear_proj_keys=False,
+                 tie_key_values=False, one_headed=False):
+        super().__init__()
+        hidden_dim = dim_head * heads
+        self.fiber = fiber
+        hidden_fiber = Fiber([(d, hidden_dim) for d, _ in fiber])
+        kv_fiber = Fiber([(d, dim_head) for d, _ in fiber]) if one_headed else hidden_fiber
+        project_out = not (heads == 1 and len(fiber.dims) == 1 and dim_head == fiber.dims[0])
+        self.scale = dim_head ** -0.5
+        self.heads, self.dim_head, self.one_headed = heads, dim_head, one_headed
+        self.linear_proj_keys = linear_proj_keys
+        conv_kw = dict(edge_dim=default(edge_dim, 0), pool=False, self_interaction=False, fourier_encode_dist=fourier_encode_dist,
+                       num_fourier_features=rel_dist_num_fourier_features, splits=splits)
+        self.to_q = LinearSE3(fiber, hidden_fiber)
+        self.to_v = ConvSE3(fiber, kv_fiber, **conv_kw)
+        assert not (linear_proj_keys and tie_key_values), 'you cannot do linear projection of keys and have shared key / values turned on at the same time'
+        if linear_proj_keys:
+            self.to_k = LinearSE3(fiber, kv_fiber)
+        elif not tie_key_values:
+            self.to_k = ConvSE3(fiber, kv_fiber, **conv_kw)
+        else:
+            self.to_k = None
+        self.to_out = LinearSE3(hidden_fiber, fiber) if project_out else nn.Identity()
+        self.use_null_kv = use_null_kv
+        if use_null_kv:
+            self.null_keys = nn.ParameterDict()
+            self.null_values = nn.ParameterDict()
+            for degree in fiber.degrees:
+                shape = (dim_head, to_order(degree)) if one_headed else (heads, dim_head, to_order(degree))
+                self.null_keys[str(degree)] = nn.Parameter(torch.zeros(*shape))
+                self.null_values[str(degree)] = nn.Parameter(torch.zeros(*shape))
+        self.attend_self = attend_self
+        if attend_self:
+            self.to_self_k = LinearSE3(fiber, kv_fiber)
+            self.to_self_v = LinearSE3(fiber, kv_fiber)
+        self.accept_global_feats = exists(global_feats_dim)
+        if self.accept_global_feats:
+            gin = Fiber.create(1, global_feats_dim)
+            gout = Fiber.create(1, kv_fiber[0])
+            self.to_global_k = LinearSE3(gin, gout)
+            self.to_global_v = LinearSE3(gin, gout)
+
+    def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
+        assert pos_emb is None, 'rotary embeddings are not part of the B200 hot path'
+        idx, nmask, _ = edge_info
+        queries = self.to_q(features)
+        k_idx = None
+        if self.linear_proj_keys:
+            values = self.to_v(features, edge_info, rel_dist, basis)
+            keys = self.to_k(features)            # node level; the attention kernel gathers through idx
+            k_idx = idx
+        elif self.to_k is None:
+            values = self.to_v(features, edge_info, rel_dist, basis)
+            keys = values
+        else:
+            keys, values = conv_forward([self.to_k, self.to_v], features, edge_info, rel_dist, basis)
+        if self.attend_self:
+            self_keys, self_values = self.to_self_k(features), self.to_self_v(features)
+        if exists(global_feats):
+            global_keys, global_values = self.to_global_k(global_feats), self.to_global_v(global_feats)
+        outputs = {}
+        for degree in features.keys():
+            kw = {}
+            if self.attend_self:
+                kw.update(self_k=self_keys[degree], self_v=self_values[degree])
+            if self.use_null_kv:
+                kw.update(null_k=self.null_keys[degree].reshape(-1, to_order(int(degree))),
+                          null_v=self.null_values[degree].reshape(-1, to_order(int(degree))))
+            if exists(global_feats) and degree == '0':
+                kw.update(global_k=global_keys[degree], global_v=global_values[degree])
+            outputs[degree] = ops.attention(queries[degree], keys[degree], values[degree], heads=self.heads, dim_head=self.dim_head,
+                                            scale=self.scale, nmask=nmask, k_idx=k_idx,
+                                            kv_heads=1 if self.one_headed else self.heads, **kw)
+        return self.to_out(outputs)
+
+
+class OneHeadedKVAttentionSE3(AttentionSE3):
+    def __init__(self, fiber, **kwargs):
+        super().__init__(fiber, one_headed=True, **kwargs)
+
+
+class AttentionBlockSE3(nn.Module):
+    """reference S:656-683"""
+
+    def __init__(self, fiber, dim_head=24, heads=8, attend_self=False, edge_dim=None, use_null_kv=False, fourier_encode_dist=False,
+                 rel_dist_num_fourier_features=4, splits=4, global_feats_dim=False, linear_proj_keys=False, tie_key_values=False,
+                 attention_klass=AttentionSE3, norm_gated_scale=False):
+        super().__init__()
+        self.attn = attention_klass(fiber, heads=heads, dim_head=dim_head, attend_self=attend_self, edge_dim=edge_dim,
+                                    use_null_kv=use_null_kv, rel_dist_num_fourier_features=rel_dist_num_fourier_features,
+                                    fourier_encode_dist=fourier_encode_dist, splits=splits, global_feats_dim=global_feats_dim,
+                                    linear_proj_keys=linear_proj_keys, tie_key_values=tie_key_values)
+        self.prenorm = NormSE3(fiber, gated_scale=norm_gated_scale)
+
+    def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
+        out = self.attn(self.prenorm(features), edge_info, rel_dist, basis, global_feats, pos_emb, mask)
+        return residual_add(out, features)
+
+
+class SequentialSequence(nn.Module):
+    """reference reversible.py:189-198"""
+
+    def __init__(self, blocks):
+        super().__init__()
+        self.blocks = blocks
+
+    def forward(self, x, **kwargs):
+        for attn, ff in self.blocks:
+            x = attn(x, **kwargs)
+            x = ff(x)
+        return x
+
+
+def masked_mean_nodes(t, mask):
+    """reference utils.py:72-80 over the node axis (return_pooled, S:1365-1367)."""
+    m = mask[(..., *((None,) * (t.dim() - mask.dim())))]
+    tot = mask.sum(dim=1)
+    tot = tot[(..., *((None,) * (t.dim() - 1 - tot.dim())))]
+    mean = t.masked_fill(~m, 0.).sum(dim=1) / tot.clamp(min=1.)
+    return mean.masked_fill(tot == 0, 0.)
+
+
+class SE3Transformer(nn.Module):
+    """Drop-in for se3_transformer_pytorch.SE3Transformer (reference S:936-1375), inference on B200.
+
+    Not carried over (raise NotImplementedError): reversible, use_egnn, rotary_position, rotary_rel_dist -- they are
+    outside the hot path named by BASELINE.json ("OUT OF SCOPE")."""
+
+    def __init__(self, *, dim, heads=8, dim_head=24, depth=2, input_degrees=1, num_degrees=None, output_degrees=1,
+                 valid_radius=1e5, reduce_dim_out=False, num_tokens=None, num_positions=None, num_edge_tokens=None, edge_dim=None,
+                 reversible=False, attend_self=True, use_null_kv=False, differentiable_coors=False, fourier_encode_dist=False,
+                 rel_dist_num_fourier_features=4, num_neighbors=float('inf'), attend_sparse_neighbors=False, num_adj_degrees=None,
+                 adj_dim=0, max_sparse_neighbors=float('inf'), dim_in=None, dim_out=None, norm_out=False, num_conv_layers=0,
+                 causal=False, splits=4, global_feats_dim=None, linear_proj_keys=False, one_headed_key_values=False,
+                 tie_key_values=False, rotary_position=False, rotary_rel_dist=False, norm_gated_scale=False, use_egnn=False,
+                 egnn_hidden_dim=32, egnn_weights_clamp_value=None, egnn_feedforward=False, hidden_fiber_dict=None,
+                 out_fiber_dict=None):
+        super().__init__()
+        for flag, name in ((reversible, 'reversible'), (use_egnn, 'use_egnn'), (rotary_position, 'rotary_position'),
+                           (rotary_rel_dist, 'rotary_rel_dist')):
+            if flag:
+                raise NotImplementedError(f'{name}=True is outside the B200 hot path of this package')
+        dim_in = default(dim_in, dim)
+        self.dim_in = dim_in if isinstance(dim_in, tuple) else (dim_in,) * input_degrees
+        self.dim = dim
+        self.token_emb = nn.Embedding(num_tokens, dim) if exists(num_tokens) else None
+        self.num_positions = num_positions
+        self.pos_emb = nn.Embedding(num_positions, dim) if exists(num_positions) else None
+        assert not (exists(num_edge_tokens) and not exists(edge_dim)), 'edge dimension (edge_dim) must be supplied if SE3 transformer is to have edge tokens'
+        self.edge_emb = nn.Embedding(num_edge_tokens, edge_dim) if exists(num_edge_tokens) else None
+        self.has_edges = exists(edge_dim) and edge_dim > 0
+        self.input_degrees = input_degrees
+        assert not (exists(num_adj_degrees) and num_adj_degrees < 1), 'make sure adjacent degrees is greater than 1'
+        assert exists(num_degrees) or exists(hidden_fiber_dict), 'either num_degrees or hidden_fiber_dict must be specified'
+        self.num_degrees = num_degrees if exists(num_degrees) else (max(hidden_fiber_dict.keys()) + 1)
+        self.output_degrees = output_degrees
+        self.differentiable_coors = differentiable_coors
+        self.valid_radius = valid_radius
+        self.num_neighbors = num_neighbors
+        self.attend_sparse_neighbors = attend_sparse_neighbors
+        self.max_sparse_neighbors = max_sparse_neighbors
+        self.num_adj_degrees = num_adj_degrees
+        self.adj_emb = nn.Embedding(num_adj_degrees + 1, adj_dim) if exists(num_adj_degrees) and adj_dim > 0 else None
+        edge_dim = (edge_dim if self.has_edges else 0) + (adj_dim if exists(self.adj_emb) else 0)
+        dim_out = default(dim_out, dim)
+        fiber_in = Fiber.create(input_degrees, dim_in)
+        fiber_hidden = Fiber(hidden_fiber_dict) if exists(hidden_fiber_dict) else Fiber.create(num_degrees, dim)
+        if exists(out_fiber_dict):
+            fiber_out = Fiber(out_fiber_dict)
+            self.output_degrees = max(out_fiber_dict.keys()) + 1
+        elif exists(output_degrees):
+            fiber_out = Fiber.create(output_degrees, dim_out)
+        else:
+            fiber_out = None
+        conv_kwargs = dict(edge_dim=edge_dim, fourier_encode_dist=fourier_encode_dist, num_fourier_features=rel_dist_num_fourier_features,
+                           splits=splits)
+        assert not (causal and not attend_self), 'attending to self must be turned on if in autoregressive mode (for the first token)'
+        self.causal = causal
+        self.conv_in = ConvSE3(fiber_in, fiber_hidden, **conv_kwargs)
+        self.convs = nn.ModuleList([])
+        for _ in range(num_conv_layers):
+            self.convs.append(nn.ModuleList([ConvSE3(fiber_hidden, fiber_hidden, **conv_kwargs),
+                                             NormSE3(fiber_hidden, gated_scale=norm_gated_scale)]))
+        self.accept_global_feats = exists(global_feats_dim)
+        self.attend_self = attend_self
+        klass = OneHeadedKVAttentionSE3 if one_headed_key_values else AttentionSE3
+        layers = nn.ModuleList([])
+        for _ in range(depth):
+            layers.append(nn.ModuleList([
+                AttentionBlockSE3(fiber_hidden, heads=heads, dim_head=dim_head, attend_self=attend_self, edge_dim=edge_dim,
+                                  fourier_encode_dist=fourier_encode_dist, rel_dist_num_fourier_features=rel_dist_num_fourier_features,
+                                  use_null_kv=use_null_kv, splits=splits, global_feats_dim=global_feats_dim,
+                                  linear_proj_keys=linear_proj_keys, attention_klass=klass, tie_key_values=tie_key_values,
+                                  norm_gated_scale=norm_gated_scale),
+                FeedForwardBlockSE3(fiber_hidden, norm_gated_scale=norm_gated_scale)]))
+        self.net = SequentialSequence(layers)
+        self.conv_out = ConvSE3(fiber_hidden, fiber_out, **conv_kwargs) if exists(fiber_out) else None
+        self.norm = NormSE3(fiber_out, gated_scale=norm_gated_scale, nonlin=nn.Identity()) if norm_out and exists(fiber_out) else nn.Identity()
+        final_fiber = default(fiber_out, fiber_hidden)
+        self.linear_out = LinearSE3(final_fiber, Fiber([(d, 1) for d, _ in final_fiber])) if reduce_dim_out else None
+
+    # ---- weights ----------------------------------------------------------------------------------------
+    def conv_modules(self):
+        return [m for m in self.modules() if isinstance(m, ConvSE3)]
+
+    def pack_weights(self, free_master=False):
+        """Pre-build the tensor-core weight images of every ConvSE3 (otherwise done lazily on the first forward)."""
+        for m in self.conv_modules():
+            m.pack_weights(free_master=free_master)
+        return self
+
+    # ---- forward ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, feats, coors, mask=None, adj_mat=None, edges=None, return_type=None, return_pooled=False,
+                neighbor_mask=None, global_feats=None):
+        assert not (self.accept_global_feats ^ exists(global_feats)), 'you cannot pass in global features unless you init the class correctly'
+        _mask = mask
+        if self.output_degrees == 1:
+            return_type = 0
+        if exists(self.token_emb):
+            feats = self.token_emb(feats)
+        if exists(self.pos_emb):
+            assert feats.shape[1] <= self.num_positions, 'feature sequence length must be less than the number of positions given at init'
+            feats = feats + self.pos_emb(torch.arange(feats.shape[1], device=feats.device)).unsqueeze(0)
+        assert not (self.attend_sparse_neighbors and not exists(adj_mat)), 'adjacency matrix (adjacency_mat) or edges (edges) must be passed in'
+        assert not (self.has_edges and not exists(edges)), 'edge embedding (num_edge_tokens & edge_dim) must be supplied if one were to train on edge types'
+        if torch.is_tensor(feats):
+            feats = {'0': feats[..., None]}
+        if torch.is_tensor(global_feats):
+            global_feats = {'0': global_feats[..., None]}
+        b, n, d = feats['0'].shape[:3]
+        device = feats['0'].device
+        if not coors.is_cuda:
+            raise RuntimeError('se3_transformer_pytorch_b200 runs on CUDA (sm_100a) only; move the model and inputs to the GPU')
+        assert d == self.dim_in[0], f'feature dimension {d} must be equal to dimension given at init {self.dim_in[0]}'
+        assert set(map(int, feats.keys())) == set(range(self.input_degrees)), f'input must have {self.input_degrees} degree'
+        feats = {k: v.float().contiguous() for k, v in feats.items()}
+        neighbors, max_sparse, valid_radius = self.num_neighbors, self.max_sparse_neighbors, self.valid_radius
+        assert self.attend_sparse_neighbors or neighbors > 0, 'you must either attend to sparsely bonded neighbors, or set number of locally attended neighbors to be greater than 0'
+
+        eye = torch.eye(n, dtype=torch.bool, device=device)
+        adj_indices = None
+        if exists(self.num_adj_degrees):                       # N-hop adjacency, reference S:1177-1191
+            if adj_mat.dim() == 2:
+                adj_mat = adj_mat.unsqueeze(0).expand(b, -1, -1).clone()
+            adj_indices = adj_mat.clone().long()
+            for ind in range(self.num_adj_degrees - 1):
+                degree = ind + 2
+                nxt = (adj_mat.float() @ adj_mat.float()) > 0
+                nxt_mask = (nxt.float() - adj_mat.float()).bool()
+                adj_indices = adj_indices.masked_fill(nxt_mask, degree)
+                adj_mat = nxt.clone()
+
+        sparse_mask = None
+        num_sparse = 0
+        if self.attend_sparse_neighbors:                       # reference S:1198-1217
+            assert exists(adj_mat), 'adjacency matrix must be passed in (keyword argument adj_mat)'
+            if adj_mat.dim() == 2:
+                adj_mat = adj_mat.unsqueeze(0).expand(b, -1, -1)
+            adj_vals = adj_mat.float().masked_fill(eye.unsqueeze(0), 0.)
+            adj_max = int(adj_vals.sum(dim=-1).max().item())
+            if max_sparse < adj_max:
+                adj_vals = adj_vals + torch.empty_like(adj_vals).uniform_(-0.01, 0.01).masked_fill(eye.unsqueeze(0), 0.)
+                adj_vals = adj_vals.masked_fill(eye.unsqueeze(0), -1.)
+            num_sparse = int(min(max_sparse, adj_max))
+            if num_sparse > 0:
+                vals, inds = adj_vals.topk(num_sparse, dim=-1)
+                sparse_mask = torch.zeros_like(adj_vals).scatter_(-1, inds, vals) > 0.5
+            else:
+                sparse_mask = torch.zeros_like(adj_vals, dtype=torch.bool)
+
+        if neighbors == 0:
+            valid_radius = 0
+        k_local = int(min(neighbors, n - 1))
+        total = int(k_local + num_sparse)
+        assert total > 0, 'you must be fetching at least 1 neighbor'
+        total = int(min(total, n - 1))
+        if exists(neighbor_mask):
+            max_nb = int(neighbor_mask.masked_fill(eye.unsqueeze(0), False).sum(dim=-1).max().item())
+            if max_nb > neighbors:
+                print(f'neighbor_mask shows maximum number of neighbors as {max_nb} but specified number of neighbors is {neighbors}')
+
+        idx, nmask, rel_pos, rel_dist = ops.knn(coors.float(), total, valid_radius, node_mask=mask, neighbor_mask=neighbor_mask,
+                                                sparse_adj=sparse_mask, causal=self.causal)
+
+        # edge features on the neighbour list (reference S:1231-1239, 1293-1294); gather first, embed after
+        e = None
+        if exists(edges):
+            if exists(self.edge_emb):
+                if edges.dim() == 2:                            # [b, n] tokens: the reference broadcasts them over rows (b == 1)
+                    assert b == 1, 'edges of shape [b, n] only broadcast for batch size 1 (as in the reference)'
+                    edges = edges.unsqueeze(1).expand(b, n, n)
+                e = self.edge_emb(edges.gather(2, idx))
+            else:
+                e = ops.gather_pairs(edges.float(), idx)
+        if exists(self.adj_emb):
+            a = self.adj_emb(adj_indices.gather(2, idx))
+            e = torch.cat((e, a), dim=-1) if exists(e) else a
+
+        basis = ops.basis_flat(rel_pos, self.num_degrees - 1)
+        edge_info = (idx, nmask, e)
+        x = self.conv_in(feats, edge_info, rel_dist=rel_dist, basis=basis)
+        for conv, nonlin in self.convs:
+            x = nonlin(x)
+            x = conv(x, edge_info, rel_dist=rel_dist, basis=basis)
+        x = self.net(x, edge_info=edge_info, rel_dist=rel_dist, basis=basis, global_feats=global_feats, pos_emb=None, mask=_mask)
+        if exists(self.conv_out):
+            x = self.conv_out(x, edge_info, rel_dist=rel_dist, basis=basis)
+        x = self.norm(x)
+        if exists(self.linear_out):
+            x = self.linear_out(x)
+            x = {k: v.squeeze(dim=2) for k, v in x.items()}
+        if return_pooled:
+            x = {k: (masked_mean_nodes(v, _mask) if exists(_mask) else v.mean(dim=1)) for k, v in x.items()}
+        if '0' in x:
+            x['0'] = x['0'].squeeze(dim=-1)
+        if exists(return_type):
+            return x[str(return_type)]
+        return x

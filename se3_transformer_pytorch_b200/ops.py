@@ -1,0 +1,335 @@
+"""ctypes binding of libse3b200.so (C ABI in include/se3b200.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op below hands raw device pointers
+and the stream handle to the hand-written sm_100a kernels.  There is NO CPU fallback: calling an op with a
+non-CUDA tensor, or without the compiled library, raises.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import build as _build
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_lock = threading.Lock()
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+_SIGNATURES = {
+    'se3_last_error': (ctypes.c_char_p, []),
+    'se3_abi_version': (c_int, []),
+    'se3_knn_fwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_int] + [c_void_p] * 4 + [c_void_p]),
+    'se3_gather_pairs_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_basis_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_void_p]),
+    'se3_radial_trunk_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'se3_tbuild_fwd': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_int64, c_int64, c_void_p, c_void_p]),
+    'se3_pairwise_simt_fwd': (c_int, [c_void_p] * 4 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
+    'se3_w3_image_bytes': (c_int64, [c_int, c_int, c_int]),
+    'se3_pack_w3': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_pairwise_tc_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
+    'se3_pairwise_tc_debug': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
+    'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load (building if the sources changed) libse3b200.so.  Raises if it cannot be built/loaded."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = _build.build()
+                handle = ctypes.CDLL(path)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)       # AttributeError if the symbol is missing -> loud failure
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError('libse3b200: ' + lib().se3_last_error().decode())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('se3_transformer_pytorch_b200 runs on CUDA (sm_100a) only: got a tensor on %s; '
+                               'there is no CPU path' % t.device)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'se3_transformer_pytorch_b200 computes in float32 (got {t.dtype})')
+    return t.contiguous()
+
+
+def _u8(t):
+    return None if t is None else t.contiguous().view(torch.uint8) if t.dtype == torch.bool else t.contiguous().to(torch.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------------
+def knn(coors, k, valid_radius, node_mask=None, neighbor_mask=None, sparse_adj=None, causal=False):
+    """Neighbour graph (reference se3_transformer_pytorch.py:1171-1294).
+    Returns idx int64 [b,n,k], mask bool [b,n,k], rel_pos [b,n,k,3], rel_dist [b,n,k]."""
+    _require_cuda(coors, node_mask, neighbor_mask, sparse_adj)
+    coors = _f32(coors)
+    b, n, _ = coors.shape
+    idx = torch.empty((b, n, k), dtype=torch.int64, device=coors.device)
+    mask = torch.empty((b, n, k), dtype=torch.uint8, device=coors.device)
+    rel_pos = torch.empty((b, n, k, 3), dtype=torch.float32, device=coors.device)
+    rel_dist = torch.empty((b, n, k), dtype=torch.float32, device=coors.device)
+    nm, nbm, sa = _u8(node_mask), _u8(neighbor_mask), _u8(sparse_adj)
+    valid_radius = float(min(valid_radius, 3.0e38))
+    with torch.cuda.device(coors.device):
+        _check(lib().se3_knn_fwd(_p(coors), _p(nm), _p(nbm), _p(sa), b, n, k, valid_radius, int(bool(causal)),
+                                 _p(idx), _p(mask), _p(rel_pos), _p(rel_dist), _stream()))
+    return idx, mask.view(torch.bool), rel_pos, rel_dist
+
+
+def gather_pairs(pair_feat, idx):
+    """pair_feat [b,n,n,e] -> [b,n,k,e] (reference utils.py:56-70 at S:1293-1294)."""
+    _require_cuda(pair_feat, idx)
+    pair_feat = _f32(pair_feat)
+    b, n, _, e = pair_feat.shape
+    k = idx.shape[-1]
+    out = torch.empty((b, n, k, e), dtype=torch.float32, device=pair_feat.device)
+    with torch.cuda.device(pair_feat.device):
+        _check(lib().se3_gather_pairs_fwd(_p(pair_feat), _p(idx.contiguous()), b, n, k, e, _p(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------------------
+_QJ = None
+
+
+def qj_table(J, d_in, d_out):
+    """Q_J tables (reference basis.py:123-138), shipped as data generated by the reference routine so that the sign
+    convention matches trained reference weights (SURVEY.md finding 6)."""
+    global _QJ
+    if _QJ is None:
+        _QJ = dict(np.load(os.path.join(_PKG, 'data', 'qj_tables.npz')))
+    return _QJ[f'{J}_{d_in}_{d_out}']
+
+
+MAX_DEGREE = 5
+
+
+class BasisPlan:
+    """CSR view of all Q_J tables for one max_degree + the per-pair output layout."""
+    _cache = {}
+
+    def __init__(self, max_degree, device):
+        if max_degree > MAX_DEGREE:
+            raise ValueError(f'max_degree {max_degree} > {MAX_DEGREE} (Q_J tables shipped up to degree {MAX_DEGREE})')
+        self.max_degree = max_degree
+        self.pairs = [(di, do) for di in range(max_degree + 1) for do in range(max_degree + 1)]
+        row_ptr, col, val = [0], [], []
+        pair_row0, pair_base = [0], []
+        base = 0
+        for di, do in self.pairs:
+            P, Q, F = 2 * do + 1, 2 * di + 1, 2 * min(di, do) + 1
+            tabs = [qj_table(abs(di - do) + f, di, do) for f in range(F)]
+            for pq in range(P * Q):
+                for f in range(F):
+                    J = abs(di - do) + f
+                    row = tabs[f][pq]
+                    thr = 1e-6 * np.abs(tabs[f]).max()
+                    for m in np.nonzero(np.abs(row) > thr)[0]:
+                        col.append(J * J + int(m))
+                        val.append(float(row[m]))
+                    row_ptr.append(len(col))
+            pair_base.append(base)
+            base += P * Q * F
+            pair_row0.append(pair_row0[-1] + P * Q * F)
+        self.rows_per_edge = base
+        self.pair_base = pair_base
+        self.pair_rows = [pair_row0[i + 1] - pair_row0[i] for i in range(len(self.pairs))]
+        mk = lambda a, dt: torch.tensor(a, dtype=dt, device=device)
+        self.row_ptr, self.col, self.val = mk(row_ptr, torch.int32), mk(col, torch.int32), mk(val, torch.float32)
+        self.pair_row0, self.pair_base_t = mk(pair_row0, torch.int32), mk(pair_base, torch.int32)
+
+    @classmethod
+    def get(cls, max_degree, device):
+        key = (max_degree, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(max_degree, device)
+        return cls._cache[key]
+
+
+def basis_flat(rel_pos, max_degree):
+    """rel_pos [..., 3] -> (flat fp32 buffer, plan); pair p lives at flat[base_p*E : (base_p+rows_p)*E] as [E, rows_p]."""
+    _require_cuda(rel_pos)
+    rel_pos = _f32(rel_pos)
+    E = rel_pos.numel() // 3
+    plan = BasisPlan.get(max_degree, rel_pos.device)
+    out = torch.empty(plan.rows_per_edge * E, dtype=torch.float32, device=rel_pos.device)
+    with torch.cuda.device(rel_pos.device):
+        _check(lib().se3_basis_fwd(_p(rel_pos), E, max_degree, _p(plan.row_ptr), _p(plan.col), _p(plan.val),
+                                   _p(plan.pair_row0), _p(plan.pair_base_t), len(plan.pairs), _p(out), _stream()))
+    return out, plan
+
+
+def get_basis(r_ij, max_degree, differentiable=False):
+    """Drop-in for the reference get_basis (basis.py:153-205): {'di,do': [..., 1, 2do+1, 1, 2di+1, f]} (forward only)."""
+    flat, plan = basis_flat(r_ij, max_degree)
+    E = r_ij.numel() // 3
+    lead = tuple(r_ij.shape[:-1])
+    out = {}
+    for (di, do), base, rows in zip(plan.pairs, plan.pair_base, plan.pair_rows):
+        out[f'{di},{do}'] = flat[base * E:(base + rows) * E].view(*lead, 1, 2 * do + 1, 1, 2 * di + 1, 2 * min(di, do) + 1)
+    return out
+
+
+def basis_pairs(flat, plan, E):
+    """{(di,do): [E, P, Q, F] view} on the flat buffer."""
+    out = {}
+    for (di, do), base, rows in zip(plan.pairs, plan.pair_base, plan.pair_rows):
+        out[(di, do)] = flat[base * E:(base + rows) * E]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K3 / K4
+# ---------------------------------------------------------------------------------------------------------
+RADIAL_MID = 128
+TILE_E, TILE_O, TILE_IF = 128, 32, 4
+
+
+def trunk_param_stride(in_dim):
+    return in_dim * RADIAL_MID + 3 * RADIAL_MID + RADIAL_MID * RADIAL_MID + 3 * RADIAL_MID
+
+
+def radial_trunk(feat, params, num_pairs, want_g=True, want_img=False):
+    """feat [E, in_dim], params [num_pairs, trunk_param_stride] -> g [pairs, E, 128] fp32 and/or the bf16 hi/lo
+    operand image (uint8 [pairs, ceil(E/128), 65536]) for the tensor-core kernel."""
+    _require_cuda(feat, params)
+    feat = _f32(feat)
+    E, in_dim = feat.shape
+    g = torch.empty((num_pairs, E, RADIAL_MID), dtype=torch.float32, device=feat.device) if want_g else None
+    img = torch.empty((num_pairs, (E + TILE_E - 1) // TILE_E, 65536), dtype=torch.uint8, device=feat.device) if want_img else None
+    with torch.cuda.device(feat.device):
+        _check(lib().se3_radial_trunk_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(g), _p(img), _stream()))
+    return g, img
+
+
+def t_numel(num_tiles, Ci, F, P):
+    nifb = (Ci * F + TILE_IF - 1) // TILE_IF
+    ph = (P + 3) // 4
+    return num_tiles * nifb * TILE_IF * ph * TILE_E * 4
+
+
+def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=None):
+    """x [b,n,Ci,2di+1], idx [b,n,k], basis_pair flat [E*P*Q*F] -> T (tile layout, see include/se3b200.h)."""
+    _require_cuda(x, idx, basis_pair)
+    x = _f32(x)
+    b, n, Ci, Q = x.shape
+    k = idx.shape[-1]
+    P, F = 2 * d_out + 1, 2 * min(d_in, d_out) + 1
+    E = b * n * k
+    n_tiles = (E + TILE_E - 1) // TILE_E
+    if tile_count is None:
+        tile_count = n_tiles - tile_begin
+    numel = t_numel(tile_count, Ci, F, P)
+    if out is None or out.numel() < numel:
+        out = torch.empty(numel, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(basis_pair), b, n, k, Ci, P, Q, F, tile_begin, tile_count,
+                                    _p(out), _stream()))
+    return out
+
+
+def pairwise_simt(g, W3, b3, T, E, Co, Ci, F, P, out, accumulate):
+    _require_cuda(g, W3, b3, T, out)
+    with torch.cuda.device(out.device):
+        _check(lib().se3_pairwise_simt_fwd(_p(g), _p(W3), _p(b3), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
+
+
+def w3_image_bytes(Co, Ci, F):
+    return lib().se3_w3_image_bytes(Co, Ci, F)
+
+
+def pack_w3(W3, b3, Co, Ci, F):
+    _require_cuda(W3, b3)
+    nbytes = w3_image_bytes(Co, Ci, F)
+    if nbytes < 0:
+        raise RuntimeError(f'pack_w3: unsupported shape Co={Co} Ci={Ci} F={F}')
+    img = torch.empty(nbytes, dtype=torch.uint8, device=W3.device)
+    with torch.cuda.device(W3.device):
+        _check(lib().se3_pack_w3(_p(_f32(W3)), _p(_f32(b3)), Co, Ci, F, _p(img), _stream()))
+    return img
+
+
+def pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
+    _require_cuda(g_img, w_img, T, out)
+    with torch.cuda.device(out.device):
+        if dump is None:
+            _check(lib().se3_pairwise_tc_fwd(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
+        else:
+            _check(lib().se3_pairwise_tc_debug(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _p(dump),
+                                               _stream()))
+
+
+def tc_supported(device, Co, P):
+    """The tcgen05 kernel needs sm_100 and Co % 32 == 0, degree_out <= 3."""
+    if os.environ.get('SE3B200_FORCE_SIMT'):
+        return False
+    if Co % TILE_O != 0 or P > 7:
+        return False
+    return torch.cuda.get_device_capability(device)[0] == 10
+
+
+def pool(x, mask):
+    """masked mean over axis 2 of x [b,n,k,...] with mask [b,n,k] (reference utils.py:72-80)."""
+    _require_cuda(x, mask)
+    x = _f32(x)
+    b, n, k = x.shape[:3]
+    C = x[0, 0, 0].numel()
+    out = torch.empty((b, n) + tuple(x.shape[3:]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().se3_pool_fwd(_p(x), _p(_u8(mask)), b * n, k, C, _p(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K5
+# ---------------------------------------------------------------------------------------------------------
+def attention(q, k, v, *, heads, dim_head, scale, nmask=None, k_idx=None, self_k=None, self_v=None, null_k=None, null_v=None,
+              global_k=None, global_v=None, kv_heads=None):
+    """One degree of AttentionSE3 / OneHeadedKVAttentionSE3 (reference S:476-517, 612-652).
+    q [b,n,H*Dh,M]; k,v [b,n,K,Ckv,M] (k may be node level [b,n,Ckv,M] with k_idx [b,n,K])."""
+    _require_cuda(q, k, v)
+    q, k, v = _f32(q), _f32(k), _f32(v)
+    b, n, _, M = q.shape
+    K = v.shape[2]
+    kv_heads = heads if kv_heads is None else kv_heads
+    G = 0 if global_k is None else global_k.shape[1]
+    cont = lambda t: None if t is None else _f32(t)
+    self_k, self_v, null_k, null_v, global_k, global_v = map(cont, (self_k, self_v, null_k, null_v, global_k, global_v))
+    out = torch.empty_like(q)
+    nm = _u8(nmask)
+    ki = None if k_idx is None else k_idx.contiguous()
+    with torch.cuda.device(q.device):
+        _check(lib().se3_attn_fwd(_p(q), _p(k), _p(v), _p(ki), _p(self_k), _p(self_v), _p(null_k), _p(null_v), _p(global_k),
+                                  _p(global_v), G, _p(nm), b, n, K, heads, dim_head, M, kv_heads, float(scale), _p(out), _stream()))
+    return out

@@ -64,3 +64,29 @@ def assert_graph_equal(idx, mask, dist, ref_idx, ref_mask, ref_dist, atol=1e-5):
     da = np.where(mask, dist, 0.0)
     db = np.where(ref_mask, ref_dist, 0.0)
     assert np.allclose(np.take_along_axis(da, oa, -1), np.take_along_axis(db, ob, -1), atol=atol)
+
+
+# ---- layout decoders for the kernel-side images (DESIGN.md "data layout") ----
+def decode_operand_image(img_u8):
+    """uint8 [..., 65536] UMMA operand image -> (hi, lo) float32 [..., 128, 128] (rows, k)."""
+    import torch
+    img = img_u8.reshape(-1, 65536).cpu().numpy()
+    as16 = img.view(np.uint16).reshape(img.shape[0], 2, 2, 128, 64)        # [tile][hi/lo][khalf][row][16B chunk * 8 + j]
+    r = np.arange(128)[:, None]
+    kk = np.arange(64)[None, :]
+    phys = ((kk >> 3) ^ (r & 7)) * 8 + (kk & 7)                            # physical element index inside the 128-byte row
+    out = np.empty((img.shape[0], 2, 128, 128), dtype=np.float32)
+    for part in range(2):
+        for kh in range(2):
+            sub = np.take_along_axis(as16[:, part, kh], np.broadcast_to(phys, (img.shape[0], 128, 64)), axis=2)
+            out[:, part, :, kh * 64:(kh + 1) * 64] = (sub.astype(np.uint32) << 16).view(np.float32)
+    return out[:, 0], out[:, 1]
+
+
+def decode_T(T, n_tiles, Ci, F, P):
+    """tile layout [tile][ifb][4][PH][128][4] -> [n_tiles*128, Ci*F, P]."""
+    nifb = (Ci * F + 3) // 4
+    ph = (P + 3) // 4
+    t = T[: n_tiles * nifb * 4 * ph * 128 * 4].reshape(n_tiles, nifb * 4, ph, 128, 4)
+    t = t.transpose(0, 3, 1, 2, 4).reshape(n_tiles * 128, nifb * 4, ph * 4)
+    return t[:, : Ci * F, :P]

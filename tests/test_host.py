@@ -1,0 +1,75 @@
+"""CPU-only checks: host logic, state_dict layout, C-ABI surface.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import MODEL_CASES, load_case, state_keys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('name', MODEL_CASES)
+def test_state_dict_layout_matches_reference(name):
+    """Same parameter names and shapes as the reference: load_state_dict interchange."""
+    from se3_transformer_pytorch_b200 import SE3Transformer
+    _, cfg = load_case(name)
+    model = SE3Transformer(**cfg['ctor'])
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == state_keys(name)
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a GPU-less box and exports everything include/se3b200.h declares."""
+    from se3_transformer_pytorch_b200 import build, ops
+    path = build.build()
+    handle = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, 'include', 'se3b200.h')).read()
+    declared = set(re.findall(r'\b(se3_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    for sym in declared:
+        assert hasattr(handle, sym), f'{sym} declared in se3b200.h but not exported'
+    assert declared == set(ops.EXPORTED_SYMBOLS)
+    assert ops.lib().se3_abi_version() == 1
+
+
+def test_constructor_assertions_match_reference():
+    from se3_transformer_pytorch_b200 import SE3Transformer
+    with pytest.raises(AssertionError):          # reference S:1048
+        SE3Transformer(dim=8)
+    with pytest.raises(AssertionError):          # reference S:1008
+        SE3Transformer(dim=8, num_degrees=2, num_edge_tokens=4)
+    with pytest.raises(AssertionError):          # reference S:1069
+        SE3Transformer(dim=8, num_degrees=2, causal=True, attend_self=False)
+    with pytest.raises(AssertionError):          # reference S:416
+        SE3Transformer(dim=8, num_degrees=2, linear_proj_keys=True, tie_key_values=True)
+    for flag in ('reversible', 'use_egnn', 'rotary_position', 'rotary_rel_dist'):
+        with pytest.raises(NotImplementedError):
+            SE3Transformer(dim=8, num_degrees=2, **{flag: True})
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors."""
+    from se3_transformer_pytorch_b200 import SE3Transformer
+    model = SE3Transformer(dim=8, heads=2, dim_head=4, depth=1, num_degrees=2, num_neighbors=4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(torch.randn(1, 8, 8), torch.randn(1, 8, 3), torch.ones(1, 8).bool())
+
+
+def test_forward_assertions_match_reference():
+    from se3_transformer_pytorch_b200 import SE3Transformer
+    model = SE3Transformer(dim=8, heads=2, dim_head=4, depth=1, num_degrees=2, num_neighbors=4, global_feats_dim=4)
+    with pytest.raises(AssertionError):          # reference S:1136
+        model(torch.randn(1, 8, 8), torch.randn(1, 8, 3))
+    model = SE3Transformer(dim=8, heads=2, dim_head=4, depth=1, num_degrees=2, num_neighbors=4, attend_sparse_neighbors=True)
+    with pytest.raises(AssertionError):          # reference S:1151
+        model(torch.randn(1, 8, 8), torch.randn(1, 8, 3))
+
+
+def test_basis_plan_shapes():
+    from se3_transformer_pytorch_b200 import ops
+    plan = ops.BasisPlan(3, 'cpu')
+    assert len(plan.pairs) == 16 and plan.rows_per_edge == 1092
+    assert plan.col.numel() == 1132                                   # non-zeros of the 44 Q_J tables
