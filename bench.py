@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark: forward point-clouds / second of the SE(3)-Transformer attention hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+Workload = BASELINE.json configs[1] ("cfg2": batch 4, N=1024, dim 512, heads 8, dim_head 64, depth 6, num_degrees 4,
+k-NN 16) per GPU; with N GPUs every rank runs its own batch of 4 clouds (weak scaling, no data-path collective) and the
+returned type-0 features are all-gathered so that every rank holds the whole batch.  A "step" is one forward pass.
+
+  value  : clouds/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e    : clouds/s through the public API with HOST inputs: pinned H2D of feats/coors/mask + forward + D2H of the result
+  roofline: the dominant kernel (fused tcgen05 pairwise kernel): algorithmic FLOPs / CUDA-event time vs measured bf16 peak
+  cpu_baseline / --impl reference: the numpy oracle (port of the reference algorithm) timed on the host cores on a
+           bounded, width-preserving sample, extrapolated by algorithmic FLOPs (the full workload needs ~79 h on CPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'cfg1': dict(ctor=dict(dim=64, depth=2, num_degrees=2, num_neighbors=8), b=1, n=32),
+    'cfg2': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=6, num_degrees=4, num_neighbors=16), b=4, n=1024),
+    'cfg3': dict(ctor=dict(dim=64, depth=2, input_degrees=1, num_degrees=2, output_degrees=2, reduce_dim_out=True, num_neighbors=16),
+                 b=2, n=256, fwd=dict(return_type=1)),
+    'cfg5': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=6, num_degrees=4, num_neighbors=32), b=8, n=2048),
+    # reduced-width variants for quick iteration (NOT the headline)
+    'cfg2_d128': dict(ctor=dict(dim=128, heads=8, dim_head=16, depth=6, num_degrees=4, num_neighbors=16), b=4, n=1024),
+    'cfg2_depth1': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=1, num_degrees=4, num_neighbors=16), b=4, n=1024),
+}
+
+
+def conv_list(ctor):
+    """[(fiber_in, fiber_out)] of every ConvSE3 in the model (reference S:1074-1113): conv_in, 2 per attention block, conv_out."""
+    dim = ctor['dim']
+    nd = ctor['num_degrees']
+    hid_attn = ctor.get('heads', 8) * ctor.get('dim_head', 24)
+    f_in = [(d, dim) for d in range(ctor.get('input_degrees', 1))]
+    f_hid = [(d, dim) for d in range(nd)]
+    f_kv = [(d, hid_attn) for d in range(nd)]
+    f_out = [(d, dim) for d in range(ctor.get('output_degrees', 1))]
+    convs = [(f_in, f_hid)]
+    for _ in range(ctor.get('depth', 2)):
+        convs += [(f_hid, f_kv), (f_hid, f_kv)]
+    convs.append((f_hid, f_out))
+    return convs
+
+
+def conv_flops(f_in, f_out, edges):
+    """Algorithmic FLOPs of one ConvSE3 on `edges` edges: radial last layer 2*128 per R element +
+    contraction 2*(2lo+1) per R element."""
+    tot = 0
+    for di, ci in f_in:
+        for do, co in f_out:
+            f = 2 * min(di, do) + 1
+            tot += edges * co * ci * f * (2 * 128 + 2 * (2 * do + 1))
+    return tot
+
+
+def forward_flops(wl):
+    c = wl['ctor']
+    k = min(c['num_neighbors'], wl['n'] - 1)
+    edges = wl['b'] * wl['n'] * k
+    return sum(conv_flops(fi, fo, edges) for fi, fo in conv_list(c))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_burst=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the numpy oracle on a bounded, width-preserving sample
+# ------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """ONE hidden->hidden ConvSE3 (pool=False: the K or V projection, >96 % of the forward's work) of the workload's widths,
+    evaluated by the oracle on a small random edge set.  prepare() builds weights/inputs once; run() is the timed part."""
+
+    def __init__(self, wl, target_flops=3e11, seed=0):
+        import numpy as np
+        from oracle import se3_oracle as O
+        self.O, self.wl = O, wl
+        c = wl['ctor']
+        nd, dim = c['num_degrees'], c['dim']
+        hid = c.get('heads', 8) * c.get('dim_head', 24)
+        k = min(c['num_neighbors'], wl['n'] - 1)
+        self.f_in = [(d, dim) for d in range(nd)]
+        self.f_out = [(d, hid) for d in range(nd)]
+        per_edge = conv_flops(self.f_in, self.f_out, 1)
+        edges = max(k, int(target_flops / per_edge))
+        n = max(k + 1, (edges + k - 1) // k)
+        rng = np.random.default_rng(seed)
+        P = {}
+        for di, ci in self.f_in:
+            for do, co in self.f_out:
+                f = 2 * min(di, do) + 1
+                pp = f'to_v.kernel_unary.({di},{do}).rp.'
+                P[pp + 'net.0.weight'] = rng.standard_normal((128, 1), dtype=np.float32)
+                P[pp + 'net.0.bias'] = np.zeros(128, np.float32)
+                P[pp + 'net.1.weight'] = np.ones(128, np.float32)
+                P[pp + 'net.1.bias'] = np.zeros(128, np.float32)
+                P[pp + 'net.3.weight'] = rng.standard_normal((128, 128), dtype=np.float32) / np.float32(11.3)
+                P[pp + 'net.3.bias'] = np.zeros(128, np.float32)
+                P[pp + 'net.4.weight'] = np.ones(128, np.float32)
+                P[pp + 'net.4.bias'] = np.zeros(128, np.float32)
+                w = rng.random((co * ci * f, 128), dtype=np.float32)
+                w -= np.float32(0.5)
+                w *= np.float32(2 / 11.3)
+                P[pp + 'net.6.weight'] = w
+                P[pp + 'net.6.bias'] = np.zeros(co * ci * f, np.float32)
+        self.P = P
+        coors = rng.standard_normal((1, n, 3)).astype(np.float32)
+        self.feats = {str(d): rng.standard_normal((1, n, ci, 2 * d + 1)).astype(np.float32) for d, ci in self.f_in}
+        self.graph = O.neighbor_graph(coors, None, num_neighbors=k)
+        self.basis = O.get_basis(self.graph['rel_pos'], nd - 1)
+        self.chunk = max(1, int(2 ** 28 // (hid * dim * (2 * (nd - 1) + 1))))
+        self.E = n * k
+        self.flops = conv_flops(self.f_in, self.f_out, self.E)
+        self.desc = (f'oracle (numpy port of the reference algorithm) on one hidden->hidden ConvSE3 (to_v) at full widths '
+                     f'(C_in={dim}, C_out={hid}, degrees {nd}, k={k}) over {self.E} edges; clouds/s extrapolated by algorithmic FLOPs '
+                     f'({self.flops:.3e} sampled vs {forward_flops(wl) / wl["b"]:.3e} per cloud)')
+
+    def run(self):
+        t0 = time.perf_counter()
+        self.O.conv_se3(self.feats, self.graph, self.basis, self.P, 'to_v.', self.f_in, self.f_out, pool=False, self_interaction=False,
+                        edge_chunk=self.chunk)
+        return time.perf_counter() - t0
+
+    def clouds_per_s(self, seconds):
+        return (self.flops / seconds) / (forward_flops(self.wl) / self.wl['b'])
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference algorithm's CPU restatement (oracle port) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    sample = CpuSample(wl, target_flops=args.cpu_flops)
+    for _ in range(min(args.warmup, 1)):
+        sample.run()
+    times = [sample.run() for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    value = sample.clouds_per_s(sec)
+    desc = sample.desc
+    line = {
+        'impl': 'reference', 'metric': 'point-clouds/sec fwd', 'value': value, 'unit': 'clouds/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, **{k: v for k, v in wl['ctor'].items()}, 'batch_per_gpu': wl['b'], 'n_points': wl['n']},
+        'cpu_baseline': {'value': value, 'unit': 'clouds/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': desc},
+        'e2e': {'value': value, 'unit': 'clouds/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        with open(self.path) as f:
+            for ln in f:
+                parts = [p.strip() for p in ln.split(',')]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(smax), 'power_w_max': max(power), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from se3_transformer_pytorch_b200 import SE3Transformer, ops
+    from se3_transformer_pytorch_b200.parallel import all_gather_batch
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(1234 + rank)
+    t_build = time.perf_counter()
+    with torch.device(dev):
+        model = SE3Transformer(**wl['ctor'])
+    model.eval()
+    model.pack_weights(free_master=True)         # tensor-core operand images; fp32 masters of net.6 released (inference)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    b, n, dim = wl['b'], wl['n'], wl['ctor']['dim']
+    fwd_kw = wl.get('fwd', {})
+    g = torch.Generator().manual_seed(99 + rank)
+    h_feats = torch.randn(b, n, dim, generator=g).pin_memory()
+    h_coors = torch.randn(b, n, 3, generator=g).pin_memory()
+    h_mask = torch.ones(b, n, dtype=torch.bool).pin_memory()
+
+    def step_resident(inputs):
+        out = model(*inputs, **fwd_kw)
+        if world > 1:
+            out = all_gather_batch(out, b * world)
+        return out
+
+    def step_e2e():
+        inputs = (h_feats.to(dev, non_blocking=True), h_coors.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True))
+        out = step_resident(inputs)
+        host = {k: v.cpu() for k, v in out.items()} if isinstance(out, dict) else out.cpu()
+        return host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), res
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # (1) end to end through the public API with host buffers
+    ms_e2e, host_out = timed(step_e2e, args.steps)
+    # (2) inputs resident in HBM; per-kernel CUDA-event brackets for the roofline
+    dev_inputs = (h_feats.to(dev), h_coors.to(dev), h_mask.to(dev))
+    launches0 = ops.LAUNCHES
+    ops.PROFILE = []
+    ms_res, _ = timed(lambda: step_resident(dev_inputs), args.steps)
+    prof, ops.PROFILE = ops.PROFILE, None
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    kern = {}
+    for name, s, e, fl, nb in prof:
+        d = kern.setdefault(name, dict(ms=0.0, flops=0, bytes=0, launches=0))
+        d['ms'] += s.elapsed_time(e)
+        d['flops'] += fl
+        d['bytes'] += nb
+        d['launches'] += 1
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    clouds = b * world * args.steps
+    value = clouds / (ms_res / 1e3)
+    e2e = clouds / (ms_e2e / 1e3)
+    h2d = h_feats.numel() * 4 + h_coors.numel() * 4 + h_mask.numel()
+    d2h = sum(v.numel() * 4 for v in host_out.values()) if isinstance(host_out, dict) else host_out.numel() * 4
+    top = max(kern.items(), key=lambda kv: kv[1]['ms'])[0] if kern else None
+    roof = None
+    if top:
+        d = kern[top]
+        if top.startswith('pairwise'):
+            ach = d['flops'] / (d['ms'] / 1e3) / 1e12
+            roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+                    'frac': ach / peaks['bf16_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
+                    'avg_launch_ms': d['ms'] / d['launches'], 'share_of_step': d['ms'] / ms_res,
+                    'note': 'achieved = algorithmic FLOPs (2*128 + 2*(2lo+1) per R element); the kernel issues 3 bf16 MMA passes per '
+                            'algorithmic GEMM FLOP for fp32 parity, so tensor-pipe work is ~3x this figure'}
+        else:
+            ach = d['bytes'] / (d['ms'] / 1e3) / 1e9
+            roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                    'traffic': None, 'peak_source': peaks['source']}
+    hbm_kernels = {}
+    for name in ('attention', 'tbuild'):
+        if name in kern and kern[name]['ms'] > 0:
+            d = kern[name]
+            ach = d['bytes'] / (d['ms'] / 1e3) / 1e9
+            hbm_kernels[name] = {'achieved_GBs': ach, 'frac_of_hbm_peak': ach / peaks['hbm_gbs'], 'ms_per_step': d['ms'] / args.steps,
+                                 'launches_per_step': d['launches'] / args.steps}
+    cpu = None
+    if not args.no_cpu_baseline:
+        sample = CpuSample(wl, target_flops=args.cpu_flops)
+        dt = sample.run()
+        cpu = {'value': sample.clouds_per_s(dt), 'unit': 'clouds/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample.desc,
+               'sample_seconds': dt}
+    line = {
+        'metric': 'point-clouds/sec fwd', 'value': value, 'unit': 'clouds/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': args.workload, **wl['ctor'], 'batch_per_gpu': b, 'global_batch': b * world, 'n_points': n,
+                   'parallelism': f'dp{world} (batch sharded, replicated weights, one all-gather of outputs)',
+                   'cache': 'inputs larger than L2: every step streams the 77 GB weight image', 'random_init': True,
+                   'flops_per_cloud': forward_flops(wl) / b, 'model_build_s': t_build},
+        'e2e': {'value': e2e, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': roof,
+        'hbm_kernels': hbm_kernels,
+        'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])},
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-flops', type=float, default=3e11, help='size of the bounded CPU sample (algorithmic FLOPs)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, wl, rank, world)
+        return
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    run_ours(args, wl, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -54,9 +54,35 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0          # number of libse3b200 kernel launches issued by this process (bench.py reports it)
+PROFILE = None        # when a list: every launch appends (kernel, start_event, end_event, algorithmic flops, algorithmic bytes)
+
+
 def _check(rc):
+    global LAUNCHES
     if rc != 0:
         raise RuntimeError('libse3b200: ' + lib().se3_last_error().decode())
+    LAUNCHES += 1
+
+
+class _timed:
+    """CUDA-event bracket on the launching stream around one kernel launch (only when PROFILE is enabled)."""
+
+    def __init__(self, name, flops=0, nbytes=0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.end.record()
+            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes))
+        return False
 
 
 def _require_cuda(*tensors):
@@ -253,7 +279,8 @@ def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=N
     numel = t_numel(tile_count, Ci, F, P)
     if out is None or out.numel() < numel:
         out = torch.empty(numel, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    nbytes = 4 * (numel + E * P * Q * F + E * Ci * Q) + 8 * E
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * F * P * Q, nbytes=nbytes):
         _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(basis_pair), b, n, k, Ci, P, Q, F, tile_begin, tile_count,
                                     _p(out), _stream()))
     return out
@@ -261,7 +288,7 @@ def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=N
 
 def pairwise_simt(g, W3, b3, T, E, Co, Ci, F, P, out, accumulate):
     _require_cuda(g, W3, b3, T, out)
-    with torch.cuda.device(out.device):
+    with torch.cuda.device(out.device), _timed('pairwise_simt', flops=2 * E * Co * Ci * F * (RADIAL_MID + P)):
         _check(lib().se3_pairwise_simt_fwd(_p(g), _p(W3), _p(b3), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
 
 
@@ -282,7 +309,10 @@ def pack_w3(W3, b3, Co, Ci, F):
 
 def pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
     _require_cuda(g_img, w_img, T, out)
-    with torch.cuda.device(out.device):
+    # algorithmic work: the radial GEMM (2*128 per R element) + the contraction with T (2*P per R element)
+    flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
+    nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
+    with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes):
         if dump is None:
             _check(lib().se3_pairwise_tc_fwd(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
         else:
@@ -329,7 +359,9 @@ def attention(q, k, v, *, heads, dim_head, scale, nmask=None, k_idx=None, self_k
     out = torch.empty_like(q)
     nm = _u8(nmask)
     ki = None if k_idx is None else k_idx.contiguous()
-    with torch.cuda.device(q.device):
+    J = K + G + (self_k is not None) + (null_k is not None)
+    nbytes = 4 * (2 * q.numel() + 2 * b * n * J * heads * dim_head * M)
+    with torch.cuda.device(q.device), _timed('attention', flops=4 * b * n * J * heads * dim_head * M, nbytes=nbytes):
         _check(lib().se3_attn_fwd(_p(q), _p(k), _p(v), _p(ki), _p(self_k), _p(self_v), _p(null_k), _p(null_v), _p(global_k),
                                   _p(global_v), G, _p(nm), b, n, K, heads, dim_head, M, kv_heads, float(scale), _p(out), _stream()))
     return out
