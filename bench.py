@@ -287,18 +287,29 @@ def run_ours(args, wl, rank, local_rank, world):
     dev_inputs = (h_feats.to(dev), h_coors.to(dev), h_mask.to(dev))
     launches0 = ops.LAUNCHES
     ops.PROFILE = []
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ms_res, _ = timed(lambda: step_resident(dev_inputs), args.steps)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     prof, ops.PROFILE = ops.PROFILE, None
     launches = ops.LAUNCHES - launches0
     clocks = sampler.stop() if rank == 0 else None
 
     kern = {}
-    for name, s, e, fl, nb in prof:
+    detail = {}
+    for name, s, e, fl, nb, tag in prof:
+        ms = s.elapsed_time(e)
         d = kern.setdefault(name, dict(ms=0.0, flops=0, bytes=0, launches=0))
-        d['ms'] += s.elapsed_time(e)
+        d['ms'] += ms
         d['flops'] += fl
         d['bytes'] += nb
         d['launches'] += 1
+        if tag:
+            t = detail.setdefault(tag, dict(ms=0.0, flops=0, launches=0))
+            t['ms'] += ms
+            t['flops'] += fl
+            t['launches'] += 1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,6 +362,8 @@ def run_ours(args, wl, rank, local_rank, world):
         'roofline': roof,
         'hbm_kernels': hbm_kernels,
         'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])},
+        'pairwise_detail': {k: {'ms_per_launch': v['ms'] / v['launches'], 'alg_tflops': v['flops'] / v['ms'] / 1e9, 'launches': v['launches']}
+                            for k, v in sorted(detail.items())},
         'cpu_baseline': cpu,
     }
     print(json.dumps(line))
@@ -367,6 +380,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-flops', type=float, default=3e11, help='size of the bounded CPU sample (algorithmic FLOPs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the resident timed steps (for ncu --profile-from-start off)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))

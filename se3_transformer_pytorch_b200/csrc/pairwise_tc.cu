@@ -19,10 +19,13 @@
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (warps 2,3 idle; the warpgroup
 // gives its registers away with setmaxnreg), warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking
 // 16 of the 32 output channels, 208 registers each).
-// Pipelines: W stages (producer -> MMA, released by tcgen05.commit), T/bias stages (producer -> epilogue),
-// TMEM accumulator double buffer (MMA -> epilogue).
+// Pipelines: a ring of four 32 KiB W slots, one per (step, k-half) unit (producer -> MMA, released by tcgen05.commit),
+// two T/bias stages (producer -> epilogue), TMEM accumulator double buffer (MMA -> epilogue).
+// CTAs are rasterised in bands (kBandM edge tiles x all channel blocks, kBandO channel blocks at a time) so that the
+// CTAs resident together share T tiles and W tiles through L2.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace se3 {
 
@@ -32,6 +35,10 @@ constexpr uint32_t kSubBytes = 16384;            // 128 rows x 64 bf16, SW128
 constexpr uint32_t kBiasBytes = 512;             // 128 fp32
 constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
 constexpr uint32_t kTmemCols = 256;              // 2 accumulator buffers x 128 columns
+constexpr uint32_t kUnitBytes = 32768;           // one k-half of a W tile: [hi 16 KiB | lo 16 KiB]
+constexpr int kWSlots = 4;
+constexpr int kBandM = 37;                       // 37 edge tiles x 4 channel blocks = 148 CTAs in flight
+constexpr int kBandO = 4;
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -129,7 +136,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// weight image packer: W3 fp32 [Co*Ci*F, 128] -> per (o-block, if-block) tile: [hi k0|hi k1|lo k0|lo k1|bias fp32 x128]
+// weight image packer: W3 fp32 [Co*Ci*F, 128] -> per (o-block, if-block) tile: [hi k0|lo k0|hi k1|lo k1|bias fp32 x128]
 // ---------------------------------------------------------------------------------------------------------
 __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __restrict__ b3, int Co, int CiF, int NIFB,
                                uint8_t* __restrict__ img) {
@@ -142,9 +149,10 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
     const float w = (ifx < CiF) ? W3[((size_t)o * CiF + ifx) * SE3_RADIAL_MID + k] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    const uint32_t off = sw128_off(r, k);
+    // W tile image: [k-half 0: hi | lo][k-half 1: hi | lo], each sub-tile 128 rows x 64 bf16, SW128
+    const uint32_t off = (uint32_t)(k >> 6) * kUnitBytes + sw128_off(r, k & 63);
     *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kSubBytes + off) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(dst + kSubBytes + off) = lo;
     if (k == 0) reinterpret_cast<float*>(dst + kImgBytes)[r] = (ifx < CiF) ? b3[(size_t)o * CiF + ifx] : 0.f;
   }
 }
@@ -161,7 +169,8 @@ struct TcSmem {                                   // offsets from the 1024-align
 template <int P, bool kDumpR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict__ w_img, const float* __restrict__ T,
-                   int64_t E, int Co, int NIFB, int accumulate, float* __restrict__ out, float* __restrict__ dumpR) {
+                   int64_t E, int Co, int NIFB, int n_mt, int n_ob, int accumulate, int dbg, float* __restrict__ out,
+                   float* __restrict__ dumpR) {
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;         // 4 (i,f) x PH x 128 edges x 16 B
   extern __shared__ uint8_t smem_raw[];
@@ -175,24 +184,40 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
   const uint32_t sBar = sBias + 2 * kBiasBytes;    // 8-byte barriers
   // barrier ids
   const uint32_t bar_a_full = sBar + 0;
-  const uint32_t bar_w_full = sBar + 8;            // [2]
-  const uint32_t bar_w_empty = sBar + 24;          // [2]
-  const uint32_t bar_t_full = sBar + 40;           // [2]
-  const uint32_t bar_t_empty = sBar + 56;          // [2]
-  const uint32_t bar_tm_full = sBar + 72;          // [2]
-  const uint32_t bar_tm_empty = sBar + 88;         // [2]
-  const uint32_t s_tmem_slot = sBar + 104;
+  const uint32_t bar_w_full = sBar + 8;            // [4]
+  const uint32_t bar_w_empty = sBar + 40;          // [4]
+  const uint32_t bar_t_full = sBar + 72;           // [2]
+  const uint32_t bar_t_empty = sBar + 88;          // [2]
+  const uint32_t bar_tm_full = sBar + 104;         // [2]
+  const uint32_t bar_tm_empty = sBar + 120;        // [2]
+  const uint32_t s_tmem_slot = sBar + 136;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t mt = blockIdx.x;
-  const int ob = blockIdx.y;
+  // band rasterisation of the 1-D grid -> (edge tile, channel block)
+  int64_t mt;
+  int ob;
+  {
+    const int64_t bid = blockIdx.x;
+    const int64_t per_band = (int64_t)kBandM * n_ob;
+    const int64_t band = bid / per_band;
+    const int64_t r = bid - band * per_band;
+    const int64_t m0 = band * kBandM;
+    const int rows = (int)min((int64_t)kBandM, (int64_t)n_mt - m0);
+    const int go = (n_ob % kBandO == 0) ? kBandO : 1;
+    const int64_t chunk = r / ((int64_t)rows * go);
+    const int64_t rr = r - chunk * rows * go;
+    ob = (int)(chunk * go + rr % go);
+    mt = m0 + rr / go;
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kWSlots; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
       mbar_init(bar_w_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 8);
       mbar_init(bar_tm_full + 8 * s, 1);
@@ -222,9 +247,15 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
       for (int s = 0; s < NIFB; ++s) {
         const int st = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-        mbar_wait(bar_w_empty + 8 * st, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_w_full + 8 * st, kImgBytes);
-        bulk_g2s(sW + st * kImgBytes, wsrc + (size_t)s * kWTileBytes, kImgBytes, bar_w_full + 8 * st);
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          const int u = 2 * s + kh;
+          const int slot = u & (kWSlots - 1);
+          const uint32_t wph = (uint32_t)(u >> 2) & 1u;
+          mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
+          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kUnitBytes);
+          bulk_g2s(sW + slot * kUnitBytes, wsrc + (size_t)s * kWTileBytes + kh * kUnitBytes, kUnitBytes, bar_w_full + 8 * slot);
+        }
         mbar_wait(bar_t_empty + 8 * st, ph ^ 1u);
         mbar_arrive_expect_tx(bar_t_full + 8 * st, kTBytes + kBiasBytes);
         bulk_g2s(sT + st * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * st);
@@ -238,30 +269,33 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
       for (int s = 0; s < NIFB; ++s) {
         const int st = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-        mbar_wait(bar_w_full + 8 * st, ph);
         mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
-        const uint32_t wbase = sW + st * kImgBytes;
         uint32_t accum = 0;
-        // pass 0: g_hi x W_hi   pass 1: g_lo x W_hi   pass 2: g_hi x W_lo
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_part = (pass == 1) ? 2u * kSubBytes : 0u;
-          const uint32_t b_part = (pass == 2) ? 2u * kSubBytes : 0u;
+        for (int kh = 0; kh < 2; ++kh) {
+          const int u = 2 * s + kh;
+          const int slot = u & (kWSlots - 1);
+          const uint32_t wph = (uint32_t)(u >> 2) & 1u;
+          mbar_wait(bar_w_full + 8 * slot, wph);
+          tc_fence_after();
+          const uint32_t wbase = sW + slot * kUnitBytes;
+          // pass 0: g_hi x W_hi   pass 1: g_lo x W_hi   pass 2: g_hi x W_lo   (this k-half)
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_part = (pass == 1) ? 2u * kSubBytes : 0u;
+            const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t ad = umma_desc_sw128(sA + a_part + kh * kSubBytes + k16 * 32);
-              const uint64_t bd = umma_desc_sw128(wbase + b_part + kh * kSubBytes + k16 * 32);
-              tc_mma_bf16(d_tmem, ad, bd, kIdesc, accum);
+              const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
+              if (!(dbg & 2)) tc_mma_bf16(d_tmem, ad, bd, kIdesc, accum);
               accum = 1;
             }
           }
+          tc_commit(bar_w_empty + 8 * slot);    // W slot free once these MMAs retire
         }
-        tc_commit(bar_w_empty + 8 * st);      // W stage free once these MMAs retire
-        tc_commit(bar_tm_full + 8 * st);      // accumulator ready for the epilogue
+        tc_commit(bar_tm_full + 8 * st);        // accumulator ready for the epilogue
       }
     }
   }
@@ -321,13 +355,18 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
               float a0, a1, a2, a3;
               unpack2(R0, a0, a1);
               unpack2(R1, a2, a3);
-              float* dr = dumpR + (((size_t)mt * gridDim.y + ob) * 128 + el) * 128 + ifl * 32 + half * 16 + b4 * 4;
+              float* dr = dumpR + (((size_t)mt * n_ob + ob) * 128 + el) * 128 + ifl * 32 + half * 16 + b4 * 4;
               dr[0] = a0; dr[1] = a1; dr[2] = a2; dr[3] = a3;
             }
+            if (!(dbg & 1)) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-              acc[b4 * 2 + 0][p] = fma2(R0, t2[p], acc[b4 * 2 + 0][p]);
-              acc[b4 * 2 + 1][p] = fma2(R1, t2[p], acc[b4 * 2 + 1][p]);
+              for (int p = 0; p < P; ++p) {
+                acc[b4 * 2 + 0][p] = fma2(R0, t2[p], acc[b4 * 2 + 0][p]);
+                acc[b4 * 2 + 1][p] = fma2(R1, t2[p], acc[b4 * 2 + 1][p]);
+              }
+            } else {
+              acc[b4 * 2 + 0][0] = add2(acc[b4 * 2 + 0][0], R0);
+              acc[b4 * 2 + 1][0] = add2(acc[b4 * 2 + 1][0], R1);
             }
           }
         }
@@ -368,7 +407,7 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
 template <int P>
 static size_t tc_smem_bytes() {
   constexpr int PH = (P + 3) / 4;
-  return 1024 + 3 * kImgBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 128;
+  return 1024 + 3 * kImgBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 160;
 }
 
 template <int P, bool kDumpR>
@@ -377,9 +416,11 @@ static int launch_tc(const void* g_img, const void* w_img, const float* T, int64
   const size_t smem = tc_smem_bytes<P>();
   auto kern = pairwise_tc_kernel<P, kDumpR>;
   SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(E, SE3_TILE_E), (unsigned)(Co / SE3_TILE_O));
-  kern<<<grid, kTcThreads, smem, s>>>(reinterpret_cast<const uint8_t*>(g_img), reinterpret_cast<const uint8_t*>(w_img), T, E, Co,
-                                      NIFB, accumulate, out, dumpR);
+  const int n_mt = (int)ceil_div(E, SE3_TILE_E), n_ob = Co / SE3_TILE_O;
+  static const int dbg = getenv("SE3B200_TC_DEBUG_MODE") ? atoi(getenv("SE3B200_TC_DEBUG_MODE")) : 0;   // timing experiments only
+  kern<<<(unsigned)((int64_t)n_mt * n_ob), kTcThreads, smem, s>>>(reinterpret_cast<const uint8_t*>(g_img),
+                                                                    reinterpret_cast<const uint8_t*>(w_img), T, E, Co, NIFB, n_mt, n_ob,
+                                                                    accumulate, dbg, out, dumpR);
   SE3_LAUNCH_OK();
   return SE3_OK;
 }
@@ -390,7 +431,7 @@ static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int
   SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_tc_fwd: bad sizes");
   SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_tc_fwd: Co=%d must be a multiple of %d (use the SIMT kernel)", Co, SE3_TILE_O);
   SE3_REQUIRE(P == 1 || P == 3 || P == 5 || P == 7, "se3_pairwise_tc_fwd: P=%d unsupported (degree_out <= 3)", P);
-  SE3_REQUIRE(ceil_div(E, SE3_TILE_E) < 2147483647ll && Co / SE3_TILE_O <= 65535, "se3_pairwise_tc_fwd: grid too large");
+  SE3_REQUIRE(ceil_div(E, SE3_TILE_E) * (Co / SE3_TILE_O) < 2147483647ll, "se3_pairwise_tc_fwd: grid too large");
   const int NIFB = (int)ceil_div((int64_t)Ci * F, SE3_TILE_IF);
   cudaStream_t s = as_stream(stream);
   switch (P) {

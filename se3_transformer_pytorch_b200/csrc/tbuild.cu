@@ -76,6 +76,66 @@ tbuild_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
   }
 }
 
+// Register-resident variant for degrees <= 3: the (P x Q) basis slice of the current frequency lives in registers, so
+// the inner loop is pure FMA + one gathered row of x per channel (no shared memory).
+template <int P, int Q>
+__global__ void __launch_bounds__(kTE)
+tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ basis,
+                  int64_t E, int64_t mt_begin, int n, int k, int Ci, int F, int ci_per_cta, float* __restrict__ T) {
+  constexpr int PH = (P + 3) / 4;
+  const int el = threadIdx.x;
+  const int64_t mt = blockIdx.x;
+  const int64_t e = (mt_begin + mt) * kTE + el;
+  const bool valid = e < E;
+  const int CiF = Ci * F;
+  const int NIFB = (CiF + SE3_TILE_IF - 1) / SE3_TILE_IF;
+  const int i0 = blockIdx.y * ci_per_cta;
+  const int i1 = min(Ci, i0 + ci_per_cta);
+  const float* xrow = x;
+  if (valid) {
+    const int64_t bn = e / k;
+    const int64_t bb = bn / n;
+    xrow = x + ((size_t)(bb * n + idx[e]) * Ci) * Q;
+  }
+  float4* Tt = reinterpret_cast<float4*>(T) + (size_t)mt * NIFB * SE3_TILE_IF * PH * kTE;
+  for (int f = 0; f < F; ++f) {
+    float B[P][Q];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) B[p][q] = valid ? basis[(size_t)e * P * Q * F + (size_t)(p * Q + q) * F + f] : 0.f;
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i) {
+      float xv[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xv[q] = valid ? xrow[(size_t)i * Q + q] : 0.f;
+      float o[PH * 4];
+#pragma unroll
+      for (int p = 0; p < PH * 4; ++p) o[p] = 0.f;
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) o[p] = fmaf(B[p][q], xv[q], o[p]);
+      const int ifx = i * F + f;
+      float4* dst = Tt + ((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE + el;
+#pragma unroll
+      for (int ph = 0; ph < PH; ++ph) dst[(size_t)ph * kTE] = make_float4(o[ph * 4], o[ph * 4 + 1], o[ph * 4 + 2], o[ph * 4 + 3]);
+    }
+  }
+  if (blockIdx.y == gridDim.y - 1) {
+    for (int ifx = CiF; ifx < NIFB * SE3_TILE_IF; ++ifx) {
+      float4* dst = Tt + ((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE + el;
+      for (int ph = 0; ph < PH; ++ph) dst[(size_t)ph * kTE] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int P, int Q>
+static void launch_reg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* basis, int64_t E, int64_t tb, int n,
+                       int k, int Ci, int F, int cpc, float* T) {
+  tbuild_reg_kernel<P, Q><<<grid, kTE, 0, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
+}
+
 }  // namespace se3
 
 extern "C" int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* basis_pair, int b, int n, int k, int Ci,
@@ -91,10 +151,18 @@ extern "C" int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* b
   int slabs = (int)std::min<int64_t>(Ci, std::max<int64_t>(1, (148 * 8) / n_mtiles));
   const int ci_per_cta = (int)ceil_div(Ci, slabs);
   slabs = (int)ceil_div(Ci, ci_per_cta);
-  const size_t smem = (size_t)P * Q * kTE * sizeof(float);
-  SE3_CUDA_OK(cudaFuncSetAttribute(tbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)n_mtiles, (unsigned)slabs);
-  tbuild_kernel<<<grid, kTE, smem, as_stream(stream)>>>(x, idx, basis_pair, E, tile_begin, n, k, Ci, P, Q, F, ci_per_cta, T);
+  cudaStream_t st = as_stream(stream);
+  if (P <= 7 && Q <= 7) {
+#define SE3_TB(PP, QQ) if (P == PP && Q == QQ) launch_reg<PP, QQ>(grid, st, x, idx, basis_pair, E, tile_begin, n, k, Ci, F, ci_per_cta, T);
+    SE3_TB(1, 1) SE3_TB(1, 3) SE3_TB(1, 5) SE3_TB(1, 7) SE3_TB(3, 1) SE3_TB(3, 3) SE3_TB(3, 5) SE3_TB(3, 7)
+    SE3_TB(5, 1) SE3_TB(5, 3) SE3_TB(5, 5) SE3_TB(5, 7) SE3_TB(7, 1) SE3_TB(7, 3) SE3_TB(7, 5) SE3_TB(7, 7)
+#undef SE3_TB
+  } else {
+    const size_t smem = (size_t)P * Q * kTE * sizeof(float);
+    SE3_CUDA_OK(cudaFuncSetAttribute(tbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tbuild_kernel<<<grid, kTE, smem, st>>>(x, idx, basis_pair, E, tile_begin, n, k, Ci, P, Q, F, ci_per_cta, T);
+  }
   SE3_LAUNCH_OK();
   return SE3_OK;
 }

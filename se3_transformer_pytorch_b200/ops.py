@@ -68,8 +68,8 @@ def _check(rc):
 class _timed:
     """CUDA-event bracket on the launching stream around one kernel launch (only when PROFILE is enabled)."""
 
-    def __init__(self, name, flops=0, nbytes=0):
-        self.name, self.flops, self.nbytes = name, flops, nbytes
+    def __init__(self, name, flops=0, nbytes=0, tag=''):
+        self.name, self.flops, self.nbytes, self.tag = name, flops, nbytes, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -81,7 +81,7 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.end.record()
-            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes))
+            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes, self.tag))
         return False
 
 
@@ -312,7 +312,7 @@ def pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
     # algorithmic work: the radial GEMM (2*128 per R element) + the contraction with T (2*P per R element)
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
     nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
-    with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes):
+    with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}'):
         if dump is None:
             _check(lib().se3_pairwise_tc_fwd(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
         else:
