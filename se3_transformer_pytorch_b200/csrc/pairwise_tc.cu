@@ -21,11 +21,16 @@
 // 16 of the 32 output channels, 208 registers each).
 // Pipelines: a ring of four 32 KiB W slots, one per (step, k-half) unit (producer -> MMA, released by tcgen05.commit),
 // two T/bias stages (producer -> epilogue), TMEM accumulator double buffer (MMA -> epilogue).
-// CTAs are rasterised in bands (kBandM edge tiles x all channel blocks, kBandO channel blocks at a time) so that the
-// CTAs resident together share T tiles and W tiles through L2.
+// Thread-block clusters of CSZ CTAs (same channel block, CSZ consecutive edge tiles) share every W unit: each CTA
+// fetches 1/CSZ of it and multicasts it into all members' shared memory (cp.async.bulk ... .multicast::cluster), and
+// a W slot is recycled when every member's MMAs have retired (tcgen05.commit ... .multicast::cluster).  This cuts the
+// per-SM L2 ingest (the measured limiter: ~80 KiB per 1536-cycle step without it) by the W share.
+// Clusters are rasterised in bands (band_m tile groups x all channel blocks, band_o channel blocks at a time) so that
+// the CTAs resident together share T tiles and W tiles through L2.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <algorithm>
 
 namespace se3 {
 
@@ -37,8 +42,7 @@ constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
 constexpr uint32_t kTmemCols = 256;              // 2 accumulator buffers x 128 columns
 constexpr uint32_t kUnitBytes = 32768;           // one k-half of a W tile: [hi 16 KiB | lo 16 KiB]
 constexpr int kWSlots = 4;
-constexpr int kBandM = 37;                       // 37 edge tiles x 4 channel blocks = 148 CTAs in flight
-constexpr int kBandO = 4;
+
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -75,10 +79,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -166,11 +186,26 @@ struct TcSmem {                                   // offsets from the 1024-align
   static constexpr uint32_t T0 = 3 * kImgBytes;
 };
 
-template <int P, bool kDumpR>
+struct TcParams {
+  const uint8_t* g_img;
+  const uint8_t* w_img;
+  const float* T;
+  float* out;
+  float* dumpR;
+  int64_t E;
+  int Co, NIFB, n_mt, n_ob, accumulate, dbg, band_m, band_o;
+};
+
+template <int P, int CSZ, bool kDumpR>
 __global__ void __launch_bounds__(kTcThreads, 1)
-pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict__ w_img, const float* __restrict__ T,
-                   int64_t E, int Co, int NIFB, int n_mt, int n_ob, int accumulate, int dbg, float* __restrict__ out,
-                   float* __restrict__ dumpR) {
+pairwise_tc_kernel(const TcParams prm) {
+  const uint8_t* __restrict__ g_img = prm.g_img;
+  const uint8_t* __restrict__ w_img = prm.w_img;
+  const float* __restrict__ T = prm.T;
+  float* __restrict__ out = prm.out;
+  float* __restrict__ dumpR = prm.dumpR;
+  const int64_t E = prm.E;
+  const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, dbg = prm.dbg;
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;         // 4 (i,f) x PH x 128 edges x 16 B
   extern __shared__ uint8_t smem_raw[];
@@ -194,28 +229,33 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // band rasterisation of the 1-D grid -> (edge tile, channel block)
+  // band rasterisation of the 1-D grid of clusters -> (edge-tile group, channel block); rank inside the cluster -> edge tile
+  const uint32_t crank = (CSZ > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
   int64_t mt;
   int ob;
+  bool active;
   {
-    const int64_t bid = blockIdx.x;
-    const int64_t per_band = (int64_t)kBandM * n_ob;
-    const int64_t band = bid / per_band;
-    const int64_t r = bid - band * per_band;
-    const int64_t m0 = band * kBandM;
-    const int rows = (int)min((int64_t)kBandM, (int64_t)n_mt - m0);
-    const int go = (n_ob % kBandO == 0) ? kBandO : 1;
+    const int64_t cid = blockIdx.x / CSZ;
+    const int n_mg = (n_mt + CSZ - 1) / CSZ;
+    const int64_t per_band = (int64_t)prm.band_m * n_ob;
+    const int64_t band = cid / per_band;
+    const int64_t r = cid - band * per_band;
+    const int64_t g0 = band * prm.band_m;
+    const int rows = (int)min((int64_t)prm.band_m, (int64_t)n_mg - g0);
+    const int go = (n_ob % prm.band_o == 0) ? prm.band_o : 1;
     const int64_t chunk = r / ((int64_t)rows * go);
     const int64_t rr = r - chunk * rows * go;
     ob = (int)(chunk * go + rr % go);
-    mt = m0 + rr / go;
+    mt = (g0 + rr / go) * CSZ + crank;
+    active = mt < n_mt;
+    if (!active) mt = n_mt - 1;               // padding CTA of the last cluster: same traffic pattern, no stores
   }
-
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
     for (int s = 0; s < kWSlots; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, CSZ);     // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
@@ -232,6 +272,7 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
   }
   tc_fence_before();
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -254,7 +295,13 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
           const uint32_t wph = (uint32_t)(u >> 2) & 1u;
           mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kUnitBytes);
-          bulk_g2s(sW + slot * kUnitBytes, wsrc + (size_t)s * kWTileBytes + kh * kUnitBytes, kUnitBytes, bar_w_full + 8 * slot);
+          if (CSZ == 1) {
+            bulk_g2s(sW + slot * kUnitBytes, wsrc + (size_t)s * kWTileBytes + kh * kUnitBytes, kUnitBytes, bar_w_full + 8 * slot);
+          } else {
+            constexpr uint32_t kShare = kUnitBytes / CSZ;      // this CTA's slice, multicast into every member's slot
+            bulk_g2s_mc(sW + slot * kUnitBytes + crank * kShare, wsrc + (size_t)s * kWTileBytes + kh * kUnitBytes + crank * kShare,
+                        kShare, bar_w_full + 8 * slot, kMask);
+          }
         }
         mbar_wait(bar_t_empty + 8 * st, ph ^ 1u);
         mbar_arrive_expect_tx(bar_t_full + 8 * st, kTBytes + kBiasBytes);
@@ -293,7 +340,8 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
               accum = 1;
             }
           }
-          tc_commit(bar_w_empty + 8 * slot);    // W slot free once these MMAs retire
+          if (CSZ == 1) tc_commit(bar_w_empty + 8 * slot);    // W slot free once these MMAs retire ...
+          else tc_commit_mc(bar_w_empty + 8 * slot, kMask);   // ... in every CTA of the cluster
         }
         tc_commit(bar_tm_full + 8 * st);        // accumulator ready for the epilogue
       }
@@ -351,7 +399,7 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
             const float4 bb = Bs[(ifl * 32 + half * 16) / 4 + b4];
             const unsigned long long R0 = add2(pack2(__uint_as_float(r[b4 * 4 + 0]), __uint_as_float(r[b4 * 4 + 1])), pack2(bb.x, bb.y));
             const unsigned long long R1 = add2(pack2(__uint_as_float(r[b4 * 4 + 2]), __uint_as_float(r[b4 * 4 + 3])), pack2(bb.z, bb.w));
-            if (kDumpR && s == 0) {
+            if (kDumpR && s == 0 && active) {
               float a0, a1, a2, a3;
               unpack2(R0, a0, a1);
               unpack2(R1, a2, a3);
@@ -379,7 +427,7 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
     }
     // write out[e, ob*32 + half*16 + (0..15), 0..P)
     const int64_t e = mt * SE3_TILE_E + el;
-    if (e < E) {
+    if (active && e < E) {
       float* dst = out + ((size_t)e * Co + (size_t)ob * SE3_TILE_O + half * 16) * P;
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
@@ -398,6 +446,7 @@ pairwise_tc_kernel(const uint8_t* __restrict__ g_img, const uint8_t* __restrict_
   }
   tc_fence_before();
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();            // no member exits while peers may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -410,19 +459,40 @@ static size_t tc_smem_bytes() {
   return 1024 + 3 * kImgBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 160;
 }
 
-template <int P, bool kDumpR>
-static int launch_tc(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int NIFB, int accumulate,
-                     float* out, float* dumpR, cudaStream_t s) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int P, int CSZ, bool kDumpR>
+static int launch_tc(const TcParams& prm, cudaStream_t s) {
   const size_t smem = tc_smem_bytes<P>();
-  auto kern = pairwise_tc_kernel<P, kDumpR>;
+  auto kern = pairwise_tc_kernel<P, CSZ, kDumpR>;
   SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_mt = (int)ceil_div(E, SE3_TILE_E), n_ob = Co / SE3_TILE_O;
-  static const int dbg = getenv("SE3B200_TC_DEBUG_MODE") ? atoi(getenv("SE3B200_TC_DEBUG_MODE")) : 0;   // timing experiments only
-  kern<<<(unsigned)((int64_t)n_mt * n_ob), kTcThreads, smem, s>>>(reinterpret_cast<const uint8_t*>(g_img),
-                                                                    reinterpret_cast<const uint8_t*>(w_img), T, E, Co, NIFB, n_mt, n_ob,
-                                                                    accumulate, dbg, out, dumpR);
-  SE3_LAUNCH_OK();
+  const int n_mg = (prm.n_mt + CSZ - 1) / CSZ;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((int64_t)n_mg * prm.n_ob * CSZ));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSZ;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SE3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prm));
   return SE3_OK;
+}
+
+template <int P, bool kDumpR>
+static int launch_tc_csz(const TcParams& prm, int csz, cudaStream_t s) {
+  switch (csz) {
+    case 1: return launch_tc<P, 1, kDumpR>(prm, s);
+    case 4: return launch_tc<P, 4, kDumpR>(prm, s);
+    default: return launch_tc<P, 2, kDumpR>(prm, s);
+  }
 }
 
 template <bool kDumpR>
@@ -431,14 +501,34 @@ static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int
   SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_tc_fwd: bad sizes");
   SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_tc_fwd: Co=%d must be a multiple of %d (use the SIMT kernel)", Co, SE3_TILE_O);
   SE3_REQUIRE(P == 1 || P == 3 || P == 5 || P == 7, "se3_pairwise_tc_fwd: P=%d unsupported (degree_out <= 3)", P);
-  SE3_REQUIRE(ceil_div(E, SE3_TILE_E) * (Co / SE3_TILE_O) < 2147483647ll, "se3_pairwise_tc_fwd: grid too large");
-  const int NIFB = (int)ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  SE3_REQUIRE((ceil_div(E, SE3_TILE_E) + 4) * (Co / SE3_TILE_O) < 2147483647ll, "se3_pairwise_tc_fwd: grid too large");
+  // tuning knobs (defaults are the shipped configuration; the env overrides exist for experiments)
+  const int dbg = env_int("SE3B200_TC_DEBUG_MODE", 0);
+  const int csz = env_int("SE3B200_TC_CLUSTER", 2);
+  const int band_m = env_int("SE3B200_TC_BANDM", 0);
+  const int band_o = env_int("SE3B200_TC_BANDO", 4);
+  TcParams prm;
+  prm.g_img = reinterpret_cast<const uint8_t*>(g_img);
+  prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  prm.T = T;
+  prm.out = out;
+  prm.dumpR = dumpR;
+  prm.E = E;
+  prm.Co = Co;
+  prm.NIFB = (int)ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  prm.n_mt = (int)ceil_div(E, SE3_TILE_E);
+  prm.n_ob = Co / SE3_TILE_O;
+  prm.accumulate = accumulate;
+  prm.dbg = dbg;
+  prm.band_o = band_o > 0 ? band_o : 1;
+  const int c = (csz == 1 || csz == 4) ? csz : 2;
+  prm.band_m = band_m > 0 ? band_m : std::max(1, 148 / (c * prm.band_o));   // one wave of 148 CTAs = band_m groups x band_o blocks
   cudaStream_t s = as_stream(stream);
   switch (P) {
-    case 1: return launch_tc<1, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
-    case 3: return launch_tc<3, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
-    case 5: return launch_tc<5, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
-    default: return launch_tc<7, kDumpR>(g_img, w_img, T, E, Co, NIFB, accumulate, out, dumpR, s);
+    case 1: return launch_tc_csz<1, kDumpR>(prm, c, s);
+    case 3: return launch_tc_csz<3, kDumpR>(prm, c, s);
+    case 5: return launch_tc_csz<5, kDumpR>(prm, c, s);
+    default: return launch_tc_csz<7, kDumpR>(prm, c, s);
   }
 }
 

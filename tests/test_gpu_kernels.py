@@ -236,6 +236,23 @@ def test_pairwise_tc_matches_fp64(di, do, Ci, Co, n, k):
     assert rel_err(out.cpu().numpy(), 2 * pr['out']) < 2e-5
 
 
+@pytest.mark.parametrize('csz', [1, 2, 4])
+def test_pairwise_tc_cluster_sizes(csz, monkeypatch):
+    """W-multicast cluster sizes 1/2/4 (incl. a padded last cluster: 5 edge tiles) give the same result."""
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.tc_supported(DEV, 64, 5):
+        pytest.skip('tensor-core path needs sm_100')
+    monkeypatch.setenv('SE3B200_TC_CLUSTER', str(csz))
+    rng = np.random.default_rng(9)
+    di, do, Ci, Co = 2, 2, 12, 64
+    pr = _pair_problem(rng, 1, 40, 15, Ci, Co, di, do)         # E = 600 -> 5 edge tiles
+    E, P, F = pr['E'], pr['P'], pr['F']
+    T = ops.tbuild(cu(pr['x']), cu(pr['idx']), cu(pr['B']).reshape(-1), di, do)
+    out = torch.zeros((E, Co, P), device=DEV)
+    ops.pairwise_tc(_g_image(cu(pr['g'])), ops.pack_w3(cu(pr['W3']), cu(pr['b3']), Co, Ci, F), T, E, Co, Ci, F, P, out, accumulate=False)
+    assert rel_err(out.cpu().numpy(), pr['out']) < 2e-5
+
+
 def test_pairwise_tc_headline_width_matches_simt():
     """BASELINE cfg2 widths (C_in = C_out = 512, degree 3 -> 3) on a small edge set: tensor-core vs SIMT fp32."""
     from se3_transformer_pytorch_b200 import ops
