@@ -506,7 +506,7 @@ static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int
   const int dbg = env_int("SE3B200_TC_DEBUG_MODE", 0);
   const int csz = env_int("SE3B200_TC_CLUSTER", 2);
   const int band_m = env_int("SE3B200_TC_BANDM", 0);
-  const int band_o = env_int("SE3B200_TC_BANDO", 4);
+  const int band_o = env_int("SE3B200_TC_BANDO", 2);
   TcParams prm;
   prm.g_img = reinterpret_cast<const uint8_t*>(g_img);
   prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
