@@ -369,61 +369,59 @@ pairwise_tc_kernel(const TcParams prm) {
       const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + st * kTBytes);
       const float4* Bs = reinterpret_cast<const float4*>(base_ptr + (sBias - base) + st * kBiasBytes);
       const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + half * 16);
+      // software pipeline inside the step: the accumulator columns of (i,f) slots 2,3 are in flight while slots 0,1
+      // are contracted, so only one tcgen05.ld latency per step is exposed
+      uint32_t r[4][16];
+      tmem_ld16(tcol + 0u, r[0]);
+      tmem_ld16(tcol + 32u, r[1]);
+      tmem_ld_wait();
+      tmem_ld16(tcol + 64u, r[2]);
+      tmem_ld16(tcol + 96u, r[3]);
 #pragma unroll
-      for (int pair = 0; pair < 2; ++pair) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(tcol + (uint32_t)((2 * pair) * 32), r0);
-        tmem_ld16(tcol + (uint32_t)((2 * pair + 1) * 32), r1);
-        tmem_ld_wait();
-        if (pair == 1) {
+      for (int ifl = 0; ifl < 4; ++ifl) {
+        if (ifl == 2) {
+          tmem_ld_wait();
           // every tcgen05.ld of this step has completed: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
         }
+        float tv[PH * 4];
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int ifl = 2 * pair + sub;
-          const uint32_t(&r)[16] = sub == 0 ? r0 : r1;
-          float tv[PH * 4];
-#pragma unroll
-          for (int h4 = 0; h4 < PH; ++h4) {
-            const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
-            tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
-          }
-          unsigned long long t2[P];
-#pragma unroll
-          for (int p = 0; p < P; ++p) t2[p] = pack2(tv[p], tv[p]);
-#pragma unroll
-          for (int b4 = 0; b4 < 4; ++b4) {
-            const float4 bb = Bs[(ifl * 32 + half * 16) / 4 + b4];
-            const unsigned long long R0 = add2(pack2(__uint_as_float(r[b4 * 4 + 0]), __uint_as_float(r[b4 * 4 + 1])), pack2(bb.x, bb.y));
-            const unsigned long long R1 = add2(pack2(__uint_as_float(r[b4 * 4 + 2]), __uint_as_float(r[b4 * 4 + 3])), pack2(bb.z, bb.w));
-            if (kDumpR && s == 0 && active) {
-              float a0, a1, a2, a3;
-              unpack2(R0, a0, a1);
-              unpack2(R1, a2, a3);
-              float* dr = dumpR + (((size_t)mt * n_ob + ob) * 128 + el) * 128 + ifl * 32 + half * 16 + b4 * 4;
-              dr[0] = a0; dr[1] = a1; dr[2] = a2; dr[3] = a3;
-            }
-            if (!(dbg & 1)) {
-#pragma unroll
-              for (int p = 0; p < P; ++p) {
-                acc[b4 * 2 + 0][p] = fma2(R0, t2[p], acc[b4 * 2 + 0][p]);
-                acc[b4 * 2 + 1][p] = fma2(R1, t2[p], acc[b4 * 2 + 1][p]);
-              }
-            } else {
-              acc[b4 * 2 + 0][0] = add2(acc[b4 * 2 + 0][0], R0);
-              acc[b4 * 2 + 1][0] = add2(acc[b4 * 2 + 1][0], R1);
-            }
-          }
+        for (int h4 = 0; h4 < PH; ++h4) {
+          const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
+          tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
         }
-        if (pair == 1) {
-          // T / bias stage fully consumed
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty + 8 * st);
+        unsigned long long t2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) t2[p] = pack2(tv[p], tv[p]);
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const float4 bb = Bs[(ifl * 32 + half * 16) / 4 + b4];
+          const unsigned long long R0 = add2(pack2(__uint_as_float(r[ifl][b4 * 4 + 0]), __uint_as_float(r[ifl][b4 * 4 + 1])), pack2(bb.x, bb.y));
+          const unsigned long long R1 = add2(pack2(__uint_as_float(r[ifl][b4 * 4 + 2]), __uint_as_float(r[ifl][b4 * 4 + 3])), pack2(bb.z, bb.w));
+          if (kDumpR && s == 0 && active) {
+            float a0, a1, a2, a3;
+            unpack2(R0, a0, a1);
+            unpack2(R1, a2, a3);
+            float* dr = dumpR + (((size_t)mt * n_ob + ob) * 128 + el) * 128 + ifl * 32 + half * 16 + b4 * 4;
+            dr[0] = a0; dr[1] = a1; dr[2] = a2; dr[3] = a3;
+          }
+          if (!(dbg & 1)) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              acc[b4 * 2 + 0][p] = fma2(R0, t2[p], acc[b4 * 2 + 0][p]);
+              acc[b4 * 2 + 1][p] = fma2(R1, t2[p], acc[b4 * 2 + 1][p]);
+            }
+          } else {
+            acc[b4 * 2 + 0][0] = add2(acc[b4 * 2 + 0][0], R0);
+            acc[b4 * 2 + 1][0] = add2(acc[b4 * 2 + 1][0], R1);
+          }
         }
       }
+      // T / bias stage fully consumed
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * st);
     }
     // write out[e, ob*32 + half*16 + (0..15), 0..P)
     const int64_t e = mt * SE3_TILE_E + el;
