@@ -68,10 +68,9 @@ int se3_basis_fwd(const float* rel_pos, int64_t E, int max_degree,
 /* Radial trunk (S:287-293) for `num_pairs` independent RadialFunc MLPs over the same edge features:
  * g = GELU(LN(W2 GELU(LN(W1 feat + b1)) + b2)), exact erf GELU, LN eps 1e-5.
  * params: per pair, contiguous floats [W1^T (in_dim x 128) | b1 | ln1_w | ln1_b | W2^T (128 x 128) | b2 | ln2_w | ln2_b].
- * out_g   : [num_pairs, E, 128] fp32 (may be NULL)
- * out_img : bf16 hi/lo UMMA operand images, [num_pairs, ceil(E/128)] tiles of 64 KiB (may be NULL); see DESIGN.md. */
+ * out_g: [num_pairs, E, 128] fp32. */
 int se3_radial_trunk_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params,
-                         float* out_g, void* out_img, void* stream);
+                         float* out_g, void* stream);
 
 /* T[e,i,f,p] = sum_q basis[e,p,q,f] * x[b, idx[e], i, q]   (the gather at S:237 fused with the basis contraction of
  * the factored form).  x: [b,n,Ci,Q], basis_pair: [E,P,Q,F], E = b*n*k.  Edge tiles
@@ -91,13 +90,14 @@ int se3_pairwise_simt_fwd(const float* g, const float* W3, const float* b3, cons
 int64_t se3_w3_image_bytes(int Co, int Ci, int F);
 int se3_pack_w3(const float* W3, const float* b3, int Co, int Ci, int F, void* image, void* stream);
 
-/* Same contraction as se3_pairwise_simt_fwd on the tcgen05 tensor cores (sm_100a only): g_img from
- * se3_radial_trunk_fwd (one pair's slice), w_img from se3_pack_w3, T from se3_tbuild_fwd. */
-int se3_pairwise_tc_fwd(const void* g_img, const void* w_img, const float* T,
+/* Same contraction as se3_pairwise_simt_fwd on the tcgen05 tensor cores (sm_100a only): g [E,128] fp32 from
+ * se3_radial_trunk_fwd (one pair's slice; split to bf16 hi/lo into tensor memory inside the kernel), w_img from
+ * se3_pack_w3, T from se3_tbuild_fwd. */
+int se3_pairwise_tc_fwd(const float* g, const void* w_img, const float* T,
                         int64_t E, int Co, int Ci, int F, int P, int accumulate, float* out, void* stream);
 /* Diagnostic for tests: as above, and dumps (R + bias) of the first (i,f) step as [ceil(E/128), Co/32, 128, 128] fp32
  * (column = if_local*32 + o_local). */
-int se3_pairwise_tc_debug(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+int se3_pairwise_tc_debug(const float* g, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
                           int P, int accumulate, float* out, float* dumpR, void* stream);
 
 /* Masked mean over the neighbour axis (utils.py:72-80): x [B, K, C] , mask [B, K] (NULL = plain mean) -> out [B, C]. */

@@ -16,10 +16,16 @@
 // kernel wants in shared memory (128-byte-swizzled K-major UMMA tiles; T in [if][p-quad][edge][4]) so every stage is
 // filled by 1-D TMA bulk copies (cp.async.bulk, completion on mbarriers) with no tensor maps.
 //
+// The A operand (the 128 x 128 tile of g, stationary for the whole CTA) lives in TENSOR MEMORY, not shared memory:
+// four epilogue warps read the fp32 rows of g, split them into bf16 hi/lo and tcgen05.st them into 128 TMEM columns;
+// every MMA is the .ts form (A from TMEM, B from smem).  Measured reason: with A in smem each M128 N128 K16 MMA pulls
+// 8 KiB of operands through the 128 B/clk shared-memory port, which (with the TMA writes and the epilogue's LDS)
+// made shared-memory bandwidth, not the tensor pipe, the limiter (profiles/r01_*).
+//
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (warps 2,3 idle; the warpgroup
 // gives its registers away with setmaxnreg), warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking
 // 16 of the 32 output channels, 208 registers each).
-// Pipelines: a ring of four 32 KiB W slots, one per (step, k-half) unit (producer -> MMA, released by tcgen05.commit),
+// Pipelines: a ring of six 32 KiB W slots, one per (step, k-half) unit (producer -> MMA, released by tcgen05.commit),
 // two T/bias stages (producer -> epilogue), TMEM accumulator double buffer (MMA -> epilogue).
 // Thread-block clusters of CSZ CTAs (same channel block, CSZ consecutive edge tiles) share every W unit: each CTA
 // fetches 1/CSZ of it and multicasts it into all members' shared memory (cp.async.bulk ... .multicast::cluster), and
@@ -39,9 +45,10 @@ constexpr uint32_t kImgBytes = 65536;            // one 128x128 hi+lo operand im
 constexpr uint32_t kSubBytes = 16384;            // 128 rows x 64 bf16, SW128
 constexpr uint32_t kBiasBytes = 512;             // 128 fp32
 constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
-constexpr uint32_t kTmemCols = 256;              // 2 accumulator buffers x 128 columns
+constexpr uint32_t kTmemCols = 512;              // 2 accumulator buffers x 128 columns + A hi/lo (64 + 64 columns)
+constexpr uint32_t kTmemAHi = 256, kTmemALo = 320;
 constexpr uint32_t kUnitBytes = 32768;           // one k-half of a W tile: [hi 16 KiB | lo 16 KiB]
-constexpr int kWSlots = 4;
+constexpr int kWSlots = 6;
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -108,6 +115,22 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -181,13 +204,12 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
 // the fused kernel
 // ---------------------------------------------------------------------------------------------------------
 struct TcSmem {                                   // offsets from the 1024-aligned base
-  static constexpr uint32_t A = 0;
-  static constexpr uint32_t W0 = kImgBytes;
-  static constexpr uint32_t T0 = 3 * kImgBytes;
+  static constexpr uint32_t W0 = 0;
+  static constexpr uint32_t T0 = kWSlots * kUnitBytes;
 };
 
 struct TcParams {
-  const uint8_t* g_img;
+  const float* g;
   const uint8_t* w_img;
   const float* T;
   float* out;
@@ -199,7 +221,7 @@ struct TcParams {
 template <int P, int CSZ, bool kDumpR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 pairwise_tc_kernel(const TcParams prm) {
-  const uint8_t* __restrict__ g_img = prm.g_img;
+  const float* __restrict__ g = prm.g;
   const uint8_t* __restrict__ w_img = prm.w_img;
   const float* __restrict__ T = prm.T;
   float* __restrict__ out = prm.out;
@@ -212,20 +234,19 @@ pairwise_tc_kernel(const TcParams prm) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t sA = base + TcSmem::A;
-  const uint32_t sW = base + TcSmem::W0;           // + st * kImgBytes
+  const uint32_t sW = base + TcSmem::W0;           // + slot * kUnitBytes
   const uint32_t sT = base + TcSmem::T0;           // + st * kTBytes
   const uint32_t sBias = sT + 2 * kTBytes;         // + st * kBiasBytes
   const uint32_t sBar = sBias + 2 * kBiasBytes;    // 8-byte barriers
   // barrier ids
   const uint32_t bar_a_full = sBar + 0;
-  const uint32_t bar_w_full = sBar + 8;            // [4]
-  const uint32_t bar_w_empty = sBar + 40;          // [4]
-  const uint32_t bar_t_full = sBar + 72;           // [2]
-  const uint32_t bar_t_empty = sBar + 88;          // [2]
-  const uint32_t bar_tm_full = sBar + 104;         // [2]
-  const uint32_t bar_tm_empty = sBar + 120;        // [2]
-  const uint32_t s_tmem_slot = sBar + 136;
+  const uint32_t bar_w_full = sBar + 8;                       // [kWSlots]
+  const uint32_t bar_w_empty = bar_w_full + 8 * kWSlots;      // [kWSlots]
+  const uint32_t bar_t_full = bar_w_empty + 8 * kWSlots;      // [2]
+  const uint32_t bar_t_empty = bar_t_full + 16;               // [2]
+  const uint32_t bar_tm_full = bar_t_empty + 16;              // [2]
+  const uint32_t bar_tm_empty = bar_tm_full + 16;             // [2]
+  const uint32_t s_tmem_slot = bar_tm_empty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,7 +273,7 @@ pairwise_tc_kernel(const TcParams prm) {
     if (!active) mt = n_mt - 1;               // padding CTA of the last cluster: same traffic pattern, no stores
   }
   if (threadIdx.x == 0) {
-    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_full, 4);                   // one arrival per A-filling warp
     for (int s = 0; s < kWSlots; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
       mbar_init(bar_w_empty + 8 * s, CSZ);     // one tcgen05.commit arrival from every CTA of the cluster
@@ -281,8 +302,6 @@ pairwise_tc_kernel(const TcParams prm) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_a_full, kImgBytes);
-      bulk_g2s(sA, g_img + (size_t)mt * kImgBytes, kImgBytes, bar_a_full);
       const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kWTileBytes;
       const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
       for (int s = 0; s < NIFB; ++s) {
@@ -291,8 +310,8 @@ pairwise_tc_kernel(const TcParams prm) {
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh) {
           const int u = 2 * s + kh;
-          const int slot = u & (kWSlots - 1);
-          const uint32_t wph = (uint32_t)(u >> 2) & 1u;
+          const int slot = u % kWSlots;
+          const uint32_t wph = (uint32_t)(u / kWSlots) & 1u;
           mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kUnitBytes);
           if (CSZ == 1) {
@@ -313,6 +332,7 @@ pairwise_tc_kernel(const TcParams prm) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_wait(bar_a_full, 0);
+      tc_fence_after();
       for (int s = 0; s < NIFB; ++s) {
         const int st = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
@@ -322,21 +342,20 @@ pairwise_tc_kernel(const TcParams prm) {
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh) {
           const int u = 2 * s + kh;
-          const int slot = u & (kWSlots - 1);
-          const uint32_t wph = (uint32_t)(u >> 2) & 1u;
+          const int slot = u % kWSlots;
+          const uint32_t wph = (uint32_t)(u / kWSlots) & 1u;
           mbar_wait(bar_w_full + 8 * slot, wph);
           tc_fence_after();
           const uint32_t wbase = sW + slot * kUnitBytes;
           // pass 0: g_hi x W_hi   pass 1: g_lo x W_hi   pass 2: g_hi x W_lo   (this k-half)
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_part = (pass == 1) ? 2u * kSubBytes : 0u;
+            const uint32_t a_tmem = tmem_base + ((pass == 1) ? kTmemALo : kTmemAHi) + (uint32_t)(kh * 32);   // 32 columns = 64 k
             const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
-              const uint64_t ad = umma_desc_sw128(sA + a_part + kh * kSubBytes + k16 * 32);
               const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
-              if (!(dbg & 2)) tc_mma_bf16(d_tmem, ad, bd, kIdesc, accum);
+              if (!(dbg & 2)) tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kIdesc, accum);
               accum = 1;
             }
           }
@@ -354,6 +373,35 @@ pairwise_tc_kernel(const TcParams prm) {
     const int half = (warp - 4) >> 2;          // which 16 of the 32 output channels
     const int el = q * 32 + lane;              // edge row inside the tile
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    if (half == 0) {
+      // ---- A operand: this thread's edge row of g (fp32) -> bf16 hi/lo pairs -> tensor memory
+      const int64_t eg = mt * SE3_TILE_E + el;
+      const float4* grow = reinterpret_cast<const float4*>(g + (size_t)(eg < E ? eg : 0) * SE3_RADIAL_MID);
+      const bool live = eg < E;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {              // 32 k values -> 16 packed columns per chunk
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float4 x = live ? grow[c * 8 + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(xs[2 * h2]), h1 = __float2bfloat16_rn(xs[2 * h2 + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(xs[2 * h2] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(xs[2 * h2 + 1] - __bfloat162float(h1));
+            hi[v * 2 + h2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[v * 2 + h2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+        }
+        tmem_st16(tmem_base + t_lane + kTmemAHi + (uint32_t)(c * 16), hi);
+        tmem_st16(tmem_base + t_lane + kTmemALo + (uint32_t)(c * 16), lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+    }
     unsigned long long acc[8][P];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -454,7 +502,7 @@ pairwise_tc_kernel(const TcParams prm) {
 template <int P>
 static size_t tc_smem_bytes() {
   constexpr int PH = (P + 3) / 4;
-  return 1024 + 3 * kImgBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 160;
+  return 1024 + kWSlots * kUnitBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 192;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -494,7 +542,7 @@ static int launch_tc_csz(const TcParams& prm, int csz, cudaStream_t s) {
 }
 
 template <bool kDumpR>
-static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+static int dispatch_tc(const float* g, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                        int accumulate, float* out, float* dumpR, void* stream) {
   SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_tc_fwd: bad sizes");
   SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_tc_fwd: Co=%d must be a multiple of %d (use the SIMT kernel)", Co, SE3_TILE_O);
@@ -506,7 +554,7 @@ static int dispatch_tc(const void* g_img, const void* w_img, const float* T, int
   const int band_m = env_int("SE3B200_TC_BANDM", 0);
   const int band_o = env_int("SE3B200_TC_BANDO", 2);
   TcParams prm;
-  prm.g_img = reinterpret_cast<const uint8_t*>(g_img);
+  prm.g = g;
   prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
   prm.T = T;
   prm.out = out;
@@ -550,13 +598,13 @@ extern "C" int se3_pack_w3(const float* W3, const float* b3, int Co, int Ci, int
   return SE3_OK;
 }
 
-extern "C" int se3_pairwise_tc_fwd(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+extern "C" int se3_pairwise_tc_fwd(const float* g, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
                                    int P, int accumulate, float* out, void* stream) {
-  return se3::dispatch_tc<false>(g_img, w_img, T, E, Co, Ci, F, P, accumulate, out, nullptr, stream);
+  return se3::dispatch_tc<false>(g, w_img, T, E, Co, Ci, F, P, accumulate, out, nullptr, stream);
 }
 
 // Diagnostic (tests only): same kernel, additionally dumps R + bias of step 0 as [edge tiles, Co/32, 128 edges, 128 cols].
-extern "C" int se3_pairwise_tc_debug(const void* g_img, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+extern "C" int se3_pairwise_tc_debug(const float* g, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
                                      int P, int accumulate, float* out, float* dumpR, void* stream) {
-  return se3::dispatch_tc<true>(g_img, w_img, T, E, Co, Ci, F, P, accumulate, out, dumpR, stream);
+  return se3::dispatch_tc<true>(g, w_img, T, E, Co, Ci, F, P, accumulate, out, dumpR, stream);
 }

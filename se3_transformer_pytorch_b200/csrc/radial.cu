@@ -2,11 +2,9 @@
 // (degree_in, degree_out) pairs of one ConvSE3 in a single launch.  The last Linear (net.6) is NOT applied here:
 // its output is consumed on-chip by the pairwise kernels.
 //
-// Output: g fp32 [pairs, E, 128] and/or the bf16 hi/lo operand image for the tcgen05 kernel:
-//   per (pair, edge tile of 128): 4 sub-tiles [hi|lo][k-half] of 128 rows x 64 bf16, 128-byte swizzled, K-major
-//   (the canonical UMMA SWIZZLE_128B layout), so the pairwise kernel can bulk-copy 64 KiB straight into smem.
+// Output: g fp32 [pairs, E, 128]; the tensor-core kernel splits its 128-edge tile of g into bf16 hi/lo on the fly
+// while loading it into tensor memory.
 #include "common.cuh"
-#include <cuda_bf16.h>
 
 namespace se3 {
 
@@ -14,13 +12,6 @@ constexpr int kMid = SE3_RADIAL_MID;  // 128
 constexpr int kTrunkEB = 32;          // edges per CTA
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-
-// byte offset of element (row r, k) inside one 128x128 (hi or lo) operand image made of two 128x64 SW128 sub-tiles
-__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
-  const int kh = k >> 6, kk = k & 63;
-  const int chunk = (kk >> 3) ^ (r & 7);
-  return (uint32_t)(kh * 16384 + r * 128 + chunk * 16 + (kk & 7) * 2);
-}
 
 // LayerNorm (eps 1e-5, biased variance) + GELU over the 128 hidden units of each edge; one warp per edge.
 __device__ __forceinline__ void ln_gelu_rows(float (*h)[kMid + 4], int ne, const float* __restrict__ w,
@@ -46,7 +37,7 @@ __device__ __forceinline__ void ln_gelu_rows(float (*h)[kMid + 4], int ne, const
 
 __global__ void __launch_bounds__(128)
 radial_trunk_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const float* __restrict__ params,
-                    int64_t param_stride, float* __restrict__ out_g, uint8_t* __restrict__ out_img, int64_t n_mtiles) {
+                    int64_t param_stride, float* __restrict__ out_g) {
   __shared__ __align__(16) float h[kTrunkEB][kMid + 4];
   __shared__ float fs[kTrunkEB][64];
   const int pair = blockIdx.y;
@@ -107,43 +98,21 @@ radial_trunk_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const
   __syncthreads();
   ln_gelu_rows(h, ne, ln2w, ln2b);
   __syncthreads();
-  if (out_g) {
-    float* og = out_g + ((size_t)pair * E + e0) * kMid;
-    for (int e = 0; e < ne; ++e) og[(size_t)e * kMid + t] = h[e][t];
-  }
-  if (out_img) {
-    // tile image: [pair][mtile] x 64 KiB = [hi: 2 x 16 KiB][lo: 2 x 16 KiB]; rows beyond E are zero.
-    for (int e = 0; e < kTrunkEB; ++e) {
-      const int64_t eg = e0 + e;
-      if (eg >= n_mtiles * SE3_TILE_E) break;
-      const float x = (e < ne) ? h[e][t] : 0.f;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-      const int64_t mt = eg / SE3_TILE_E;
-      const int r = (int)(eg % SE3_TILE_E);
-      uint8_t* tile = out_img + ((size_t)pair * n_mtiles + mt) * 65536;
-      const uint32_t off = sw128_offset(r, t);
-      *reinterpret_cast<__nv_bfloat16*>(tile + off) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(tile + 32768 + off) = lo;
-    }
-  }
+  float* og = out_g + ((size_t)pair * E + e0) * kMid;
+  for (int e = 0; e < ne; ++e) og[(size_t)e * kMid + t] = h[e][t];
 }
 
 }  // namespace se3
 
 extern "C" int se3_radial_trunk_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params,
-                                    float* out_g, void* out_img, void* stream) {
+                                    float* out_g, void* stream) {
   using namespace se3;
   SE3_REQUIRE(E > 0 && num_pairs > 0, "se3_radial_trunk_fwd: bad sizes");
   SE3_REQUIRE(in_dim >= 1 && in_dim <= 64, "se3_radial_trunk_fwd: in_dim %d unsupported (1..64)", in_dim);
-  SE3_REQUIRE(out_g || out_img, "se3_radial_trunk_fwd: no output requested");
-  const int64_t n_mtiles = ceil_div(E, SE3_TILE_E);
+  SE3_REQUIRE(out_g != nullptr, "se3_radial_trunk_fwd: no output buffer");
   const int64_t param_stride = (int64_t)in_dim * kMid + 3 * kMid + kMid * kMid + 3 * kMid;
-  // the image path also has to zero-fill the padded rows of the last tile: cover them with the grid
-  const int64_t e_cover = out_img ? n_mtiles * SE3_TILE_E : E;
-  dim3 grid((unsigned)ceil_div(e_cover, kTrunkEB), (unsigned)num_pairs);
-  radial_trunk_kernel<<<grid, 128, 0, as_stream(stream)>>>(feat, E, in_dim, params, param_stride, out_g,
-                                                            reinterpret_cast<uint8_t*>(out_img), n_mtiles);
+  dim3 grid((unsigned)ceil_div(E, kTrunkEB), (unsigned)num_pairs);
+  radial_trunk_kernel<<<grid, 128, 0, as_stream(stream)>>>(feat, E, in_dim, params, param_stride, out_g);
   SE3_LAUNCH_OK();
   return SE3_OK;
 }

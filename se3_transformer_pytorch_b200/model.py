@@ -249,10 +249,9 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         feat = conv.edge_features(edge_info, rel_dist)
         assert feat.shape[-1] == conv.in_dim, f'edge feature width {feat.shape[-1]} != {conv.in_dim}'
         use_tc = {p: (p in pk['images']) for p in conv.pairs}
-        any_tc, any_simt = any(use_tc.values()), not all(use_tc.values())
-        g, img = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs), want_g=any_simt, want_img=any_tc)
+        g = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs))
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
-        states.append(dict(conv=conv, pk=pk, g=g, img=img, outs=outs, use_tc=use_tc))
+        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=use_tc))
 
     # chunk over edge tiles so that the largest T block fits the workspace
     worst = max(ops.t_numel(1, mi, to_order(min(di, do)), to_order(do)) * 4
@@ -274,7 +273,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                     conv = st['conv']
                     out = st['outs'][do][e0:e0 + ec]
                     if st['use_tc'][(di, do)]:
-                        ops.pairwise_tc(st['img'][pi, t0:t0 + tc], st['pk']['images'][(di, do)], workspace, ec, mo, mi, Fq, P,
+                        ops.pairwise_tc(st['g'][pi, e0:e0 + ec], st['pk']['images'][(di, do)], workspace, ec, mo, mi, Fq, P,
                                         out, accumulate=not first)
                     else:
                         lin = conv.kernel_unary[f'({di},{do})'].rp.net['6']

@@ -25,7 +25,7 @@ _SIGNATURES = {
     'se3_knn_fwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_int] + [c_void_p] * 4 + [c_void_p]),
     'se3_gather_pairs_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_basis_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_void_p]),
-    'se3_radial_trunk_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'se3_radial_trunk_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'se3_tbuild_fwd': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_int64, c_int64, c_void_p, c_void_p]),
     'se3_pairwise_simt_fwd': (c_int, [c_void_p] * 4 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
     'se3_w3_image_bytes': (c_int64, [c_int, c_int, c_int]),
@@ -246,17 +246,15 @@ def trunk_param_stride(in_dim):
     return in_dim * RADIAL_MID + 3 * RADIAL_MID + RADIAL_MID * RADIAL_MID + 3 * RADIAL_MID
 
 
-def radial_trunk(feat, params, num_pairs, want_g=True, want_img=False):
-    """feat [E, in_dim], params [num_pairs, trunk_param_stride] -> g [pairs, E, 128] fp32 and/or the bf16 hi/lo
-    operand image (uint8 [pairs, ceil(E/128), 65536]) for the tensor-core kernel."""
+def radial_trunk(feat, params, num_pairs):
+    """feat [E, in_dim], params [num_pairs, trunk_param_stride] -> g [pairs, E, 128] fp32."""
     _require_cuda(feat, params)
     feat = _f32(feat)
     E, in_dim = feat.shape
-    g = torch.empty((num_pairs, E, RADIAL_MID), dtype=torch.float32, device=feat.device) if want_g else None
-    img = torch.empty((num_pairs, (E + TILE_E - 1) // TILE_E, 65536), dtype=torch.uint8, device=feat.device) if want_img else None
+    g = torch.empty((num_pairs, E, RADIAL_MID), dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
-        _check(lib().se3_radial_trunk_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(g), _p(img), _stream()))
-    return g, img
+        _check(lib().se3_radial_trunk_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(g), _stream()))
+    return g
 
 
 def t_numel(num_tiles, Ci, F, P):
@@ -307,16 +305,16 @@ def pack_w3(W3, b3, Co, Ci, F):
     return img
 
 
-def pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
-    _require_cuda(g_img, w_img, T, out)
+def pairwise_tc(g, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
+    _require_cuda(g, w_img, T, out)
     # algorithmic work: the radial GEMM (2*128 per R element) + the contraction with T (2*P per R element)
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
     nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
     with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}'):
         if dump is None:
-            _check(lib().se3_pairwise_tc_fwd(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
+            _check(lib().se3_pairwise_tc_fwd(_p(g), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
         else:
-            _check(lib().se3_pairwise_tc_debug(_p(g_img), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _p(dump),
+            _check(lib().se3_pairwise_tc_debug(_p(g), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _p(dump),
                                                _stream()))
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, load_case, rel_err, decode_operand_image, decode_T, assert_graph_equal
+from helpers import GOLDEN, load_case, rel_err, decode_T, assert_graph_equal
 from oracle import se3_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -123,18 +123,10 @@ def test_radial_trunk(in_dim, E):
                                      P['net.3.weight'].T.ravel(), P['net.3.bias'], P['net.4.weight'], P['net.4.bias']]))
     params = cu(np.stack(packs))
     assert params.shape[1] == ops.trunk_param_stride(in_dim)
-    g, img = ops.radial_trunk(cu(feat), params, pairs, want_g=True, want_img=True)
-    g = g.cpu().numpy()
-    n_tiles = (E + 127) // 128
-    hi, lo = decode_operand_image(img)
-    hi = hi.reshape(pairs, n_tiles * 128, 128)
-    lo = lo.reshape(pairs, n_tiles * 128, 128)
+    g = ops.radial_trunk(cu(feat), params, pairs).cpu().numpy()
     for p in range(pairs):
         ref = O.radial_trunk(feat.astype(np.float64), {k: v.astype(np.float64) for k, v in Ps[p].items()}, '')
         assert rel_err(g[p], ref) < 5e-6
-        rec = hi[p, :E] + lo[p, :E]
-        assert np.abs(rec - g[p]).max() <= 2.0 ** -16 * np.abs(g[p]).max()      # bf16 hi+lo split keeps ~16 mantissa bits
-        assert np.all(hi[p, E:] == 0) and np.all(lo[p, E:] == 0)                # padded rows are zero
 
 
 # ------------------------------------------------------------------ K4
@@ -185,27 +177,6 @@ def test_pairwise_simt(di, do, Ci, Co):
     assert rel_err(out.cpu().numpy(), 2 * pr['out']) < 5e-6
 
 
-def _g_image(g):
-    """host-side reference of the operand image the trunk kernel writes: tiles of [hi|lo] bf16, swizzled."""
-    from se3_transformer_pytorch_b200 import ops
-    E = g.shape[0]
-    # use the trunk kernel's own writer through an identity-free path is not possible; build with torch instead
-    n_tiles = (E + 127) // 128
-    gp = torch.zeros((n_tiles * 128, 128), device=DEV)
-    gp[:E] = g
-    hi = gp.to(torch.bfloat16)
-    lo = (gp - hi.float()).to(torch.bfloat16)
-    r = torch.arange(128, device=DEV)[:, None]
-    k = torch.arange(128, device=DEV)[None, :]
-    kk = k & 63
-    off = (k >> 6) * 16384 + r * 128 + (((kk >> 3) ^ (r & 7)) * 16) + (kk & 7) * 2        # byte offset inside a 32 KiB part
-    img = torch.zeros((n_tiles, 2, 16384), dtype=torch.int16, device=DEV)
-    for part, src in enumerate((hi, lo)):
-        v = src.view(torch.int16).view(n_tiles, 128, 128)
-        img[:, part].scatter_(1, (off // 2).reshape(1, -1).expand(n_tiles, -1), v.reshape(n_tiles, -1))
-    return img.view(torch.uint8).reshape(n_tiles, 65536)
-
-
 @pytest.mark.parametrize('di,do,Ci,Co,n,k', [(0, 0, 8, 32, 16, 8), (1, 1, 5, 32, 16, 9), (3, 3, 4, 64, 20, 13), (2, 3, 6, 32, 32, 8),
                                              (1, 0, 33, 96, 16, 8), (3, 2, 16, 32, 7, 5)])
 def test_pairwise_tc_matches_fp64(di, do, Ci, Co, n, k):
@@ -218,11 +189,11 @@ def test_pairwise_tc_matches_fp64(di, do, Ci, Co, n, k):
     E, P, F = pr['E'], pr['P'], pr['F']
     T = ops.tbuild(cu(pr['x']), cu(pr['idx']), cu(pr['B']).reshape(-1), di, do)
     w_img = ops.pack_w3(cu(pr['W3']), cu(pr['b3']), Co, Ci, F)
-    g_img = _g_image(cu(pr['g']))
+    g_dev = cu(pr['g'])
     n_tiles = (E + 127) // 128
     out = torch.full((E, Co, P), 3.0, device=DEV)
     dump = torch.zeros((n_tiles, Co // 32, 128, 128), device=DEV)
-    ops.pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate=False, dump=dump)
+    ops.pairwise_tc(g_dev, w_img, T, E, Co, Ci, F, P, out, accumulate=False, dump=dump)
     torch.cuda.synchronize()
     # R of step 0: column = if_local*32 + o_local for (i,f) 0..3 of each 32-channel block
     R = pr['R'].reshape(E, Co, Ci * F)
@@ -232,7 +203,7 @@ def test_pairwise_tc_matches_fp64(di, do, Ci, Co, n, k):
             got = d[:, ob, :, ifl * 32:(ifl + 1) * 32].reshape(n_tiles * 128, 32)[:E]
             assert rel_err(got, R[:, ob * 32:(ob + 1) * 32, ifl]) < 2e-5, (ob, ifl)
     assert rel_err(out.cpu().numpy(), pr['out']) < 2e-5
-    ops.pairwise_tc(g_img, w_img, T, E, Co, Ci, F, P, out, accumulate=True)
+    ops.pairwise_tc(g_dev, w_img, T, E, Co, Ci, F, P, out, accumulate=True)
     assert rel_err(out.cpu().numpy(), 2 * pr['out']) < 2e-5
 
 
@@ -249,7 +220,7 @@ def test_pairwise_tc_cluster_sizes(csz, monkeypatch):
     E, P, F = pr['E'], pr['P'], pr['F']
     T = ops.tbuild(cu(pr['x']), cu(pr['idx']), cu(pr['B']).reshape(-1), di, do)
     out = torch.zeros((E, Co, P), device=DEV)
-    ops.pairwise_tc(_g_image(cu(pr['g'])), ops.pack_w3(cu(pr['W3']), cu(pr['b3']), Co, Ci, F), T, E, Co, Ci, F, P, out, accumulate=False)
+    ops.pairwise_tc(cu(pr['g']), ops.pack_w3(cu(pr['W3']), cu(pr['b3']), Co, Ci, F), T, E, Co, Ci, F, P, out, accumulate=False)
     assert rel_err(out.cpu().numpy(), pr['out']) < 2e-5
 
 
@@ -271,11 +242,11 @@ def test_pairwise_tc_headline_width_matches_simt():
     ref = torch.empty(E, C, P, device=DEV)
     ops.pairwise_simt(g, W3, b3, T, E, C, C, F, P, ref, accumulate=False)
     out = torch.empty(E, C, P, device=DEV)
-    ops.pairwise_tc(_g_image(g), ops.pack_w3(W3, b3, C, C, F), T, E, C, C, F, P, out, accumulate=False)
+    ops.pairwise_tc(g, ops.pack_w3(W3, b3, C, C, F), T, E, C, C, F, P, out, accumulate=False)
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
     # linearity in T (size independent property): out(2T) == 2 out(T)
     out2 = torch.empty(E, C, P, device=DEV)
-    ops.pairwise_tc(_g_image(g), ops.pack_w3(W3, b3, C, C, F), 2 * T, E, C, C, F, P, out2, accumulate=False)
+    ops.pairwise_tc(g, ops.pack_w3(W3, b3, C, C, F), 2 * T, E, C, C, F, P, out2, accumulate=False)
     assert rel_err(out2.cpu().numpy(), 2 * out.cpu().numpy()) < 1e-6
 
 
