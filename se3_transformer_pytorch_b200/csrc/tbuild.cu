@@ -76,14 +76,17 @@ tbuild_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
   }
 }
 
-// Register-resident variant for degrees <= 3: the (P x Q) basis slice of the current frequency lives in registers, so
-// the inner loop is pure FMA + one gathered row of x per channel (no shared memory).
+// Register-resident variant for degrees <= 3: thread = (edge, quad of output components p); its 4 x Q slice of the
+// basis for the current frequency lives in registers, four input channels are in flight per iteration (independent
+// gathered loads -> FMAs -> one coalesced 16-byte store each), no shared memory.
 template <int P, int Q>
-__global__ void __launch_bounds__(kTE)
+__global__ void __launch_bounds__(kTE * ((P + 3) / 4))
 tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ basis,
                   int64_t E, int64_t mt_begin, int n, int k, int Ci, int F, int ci_per_cta, float* __restrict__ T) {
   constexpr int PH = (P + 3) / 4;
+  constexpr int UN = 4;
   const int el = threadIdx.x;
+  const int ph = threadIdx.y;
   const int64_t mt = blockIdx.x;
   const int64_t e = (mt_begin + mt) * kTE + el;
   const bool valid = e < E;
@@ -97,43 +100,46 @@ tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, 
     const int64_t bb = bn / n;
     xrow = x + ((size_t)(bb * n + idx[e]) * Ci) * Q;
   }
-  float4* Tt = reinterpret_cast<float4*>(T) + (size_t)mt * NIFB * SE3_TILE_IF * PH * kTE;
+  float4* Tt = reinterpret_cast<float4*>(T) + (size_t)mt * NIFB * SE3_TILE_IF * PH * kTE + (size_t)ph * kTE + el;
   for (int f = 0; f < F; ++f) {
-    float B[P][Q];
+    float B[4][Q];
 #pragma unroll
-    for (int p = 0; p < P; ++p)
+    for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-      for (int q = 0; q < Q; ++q) B[p][q] = valid ? basis[(size_t)e * P * Q * F + (size_t)(p * Q + q) * F + f] : 0.f;
-#pragma unroll 2
-    for (int i = i0; i < i1; ++i) {
-      float xv[Q];
+      for (int q = 0; q < Q; ++q) {
+        const int p = ph * 4 + pp;
+        B[pp][q] = (valid && p < P) ? basis[(size_t)e * P * Q * F + (size_t)(p * Q + q) * F + f] : 0.f;
+      }
+    for (int i = i0; i < i1; i += UN) {
+      float xv[UN][Q];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) xv[q] = valid ? xrow[(size_t)i * Q + q] : 0.f;
-      float o[PH * 4];
+      for (int u = 0; u < UN; ++u)
 #pragma unroll
-      for (int p = 0; p < PH * 4; ++p) o[p] = 0.f;
+        for (int q = 0; q < Q; ++q) xv[u][q] = (valid && i + u < i1) ? xrow[(size_t)(i + u) * Q + q] : 0.f;
 #pragma unroll
-      for (int p = 0; p < P; ++p)
+      for (int u = 0; u < UN; ++u) {
+        if (i + u < i1) {
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < Q; ++q) o[p] = fmaf(B[p][q], xv[q], o[p]);
-      const int ifx = i * F + f;
-      float4* dst = Tt + ((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE + el;
+          for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-      for (int ph = 0; ph < PH; ++ph) dst[(size_t)ph * kTE] = make_float4(o[ph * 4], o[ph * 4 + 1], o[ph * 4 + 2], o[ph * 4 + 3]);
+            for (int q = 0; q < Q; ++q) o[pp] = fmaf(B[pp][q], xv[u][q], o[pp]);
+          const int ifx = (i + u) * F + f;
+          Tt[((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
     }
   }
   if (blockIdx.y == gridDim.y - 1) {
-    for (int ifx = CiF; ifx < NIFB * SE3_TILE_IF; ++ifx) {
-      float4* dst = Tt + ((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE + el;
-      for (int ph = 0; ph < PH; ++ph) dst[(size_t)ph * kTE] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int ifx = CiF; ifx < NIFB * SE3_TILE_IF; ++ifx)
+      Tt[((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 template <int P, int Q>
 static void launch_reg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* basis, int64_t E, int64_t tb, int n,
                        int k, int Ci, int F, int cpc, float* T) {
-  tbuild_reg_kernel<P, Q><<<grid, kTE, 0, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
+  tbuild_reg_kernel<P, Q><<<grid, dim3(kTE, (P + 3) / 4), 0, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
 }
 
 }  // namespace se3
