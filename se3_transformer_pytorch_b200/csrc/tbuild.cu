@@ -76,17 +76,22 @@ tbuild_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
   }
 }
 
-// Register-resident variant for degrees <= 3: thread = (edge, quad of output components p); its 4 x Q slice of the
-// basis for the current frequency lives in registers, four input channels are in flight per iteration (independent
-// gathered loads -> FMAs -> one coalesced 16-byte store each), no shared memory.
+// Fast variant for degrees <= 3.  The whole per-edge basis block ([P][Q][F] floats x 128 edges, <= 172 KiB) is staged
+// in shared memory once per CTA as Bs[r][edge]; thread = (edge, channel lane).  Each input channel row x[j, i, :] is
+// gathered exactly once (Q registers) and produces all F * ceil(P/4) output quads with conflict-free LDS + FMA and one
+// coalesced 16-byte store per quad.
+constexpr int kTbLanes = 4;     // channel lanes per edge (512 threads per CTA)
+
 template <int P, int Q>
-__global__ void __launch_bounds__(kTE * ((P + 3) / 4))
+__global__ void __launch_bounds__(kTE * kTbLanes, 1)
 tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ basis,
-                  int64_t E, int64_t mt_begin, int n, int k, int Ci, int F, int ci_per_cta, float* __restrict__ T) {
+                  int64_t E, int64_t mt_begin, int n, int k, int Ci, int F_rt, int ci_per_cta, float* __restrict__ T) {
   constexpr int PH = (P + 3) / 4;
-  constexpr int UN = 4;
+  constexpr int F = (P < Q) ? P : Q;                     // 2*min(li,lo)+1
+  constexpr int R = P * Q * F;
+  extern __shared__ float Bs[];                          // [R][kTE]
   const int el = threadIdx.x;
-  const int ph = threadIdx.y;
+  const int lane_c = threadIdx.y;
   const int64_t mt = blockIdx.x;
   const int64_t e = (mt_begin + mt) * kTE + el;
   const bool valid = e < E;
@@ -94,52 +99,56 @@ tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, 
   const int NIFB = (CiF + SE3_TILE_IF - 1) / SE3_TILE_IF;
   const int i0 = blockIdx.y * ci_per_cta;
   const int i1 = min(Ci, i0 + ci_per_cta);
+  // stage the basis: every thread copies a quarter of its own edge's block
+  {
+    const float* bp = basis + (size_t)(valid ? e : 0) * R;
+    for (int r = lane_c; r < R; r += kTbLanes) Bs[r * kTE + el] = valid ? bp[r] : 0.f;
+  }
   const float* xrow = x;
   if (valid) {
     const int64_t bn = e / k;
     const int64_t bb = bn / n;
     xrow = x + ((size_t)(bb * n + idx[e]) * Ci) * Q;
   }
-  float4* Tt = reinterpret_cast<float4*>(T) + (size_t)mt * NIFB * SE3_TILE_IF * PH * kTE + (size_t)ph * kTE + el;
-  for (int f = 0; f < F; ++f) {
-    float B[4][Q];
+  float4* Tt = reinterpret_cast<float4*>(T) + (size_t)mt * NIFB * SE3_TILE_IF * PH * kTE + el;
+  __syncthreads();
+  for (int i = i0 + lane_c; i < i1; i += kTbLanes) {
+    float xv[Q];
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp)
+    for (int q = 0; q < Q; ++q) xv[q] = valid ? xrow[(size_t)i * Q + q] : 0.f;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int p = ph * 4 + pp;
-        B[pp][q] = (valid && p < P) ? basis[(size_t)e * P * Q * F + (size_t)(p * Q + q) * F + f] : 0.f;
-      }
-    for (int i = i0; i < i1; i += UN) {
-      float xv[UN][Q];
+    for (int f = 0; f < F; ++f) {
+      const int ifx = i * F + f;
+      float4* dst = Tt + ((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE;
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
+      for (int ph = 0; ph < PH; ++ph) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < Q; ++q) xv[u][q] = (valid && i + u < i1) ? xrow[(size_t)(i + u) * Q + q] : 0.f;
+        for (int pp = 0; pp < 4; ++pp) {
+          const int p = ph * 4 + pp;
+          if (p < P) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        if (i + u < i1) {
-          float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp)
-#pragma unroll
-            for (int q = 0; q < Q; ++q) o[pp] = fmaf(B[pp][q], xv[u][q], o[pp]);
-          const int ifx = (i + u) * F + f;
-          Tt[((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE] = make_float4(o[0], o[1], o[2], o[3]);
+            for (int q = 0; q < Q; ++q) o[pp] = fmaf(Bs[((p * Q + q) * F + f) * kTE + el], xv[q], o[pp]);
+          }
         }
+        dst[(size_t)ph * kTE] = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   }
-  if (blockIdx.y == gridDim.y - 1) {
+  if (blockIdx.y == gridDim.y - 1 && lane_c == 0) {
     for (int ifx = CiF; ifx < NIFB * SE3_TILE_IF; ++ifx)
-      Tt[((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH * kTE] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ph = 0; ph < PH; ++ph)
+        Tt[(((size_t)(ifx / SE3_TILE_IF) * SE3_TILE_IF + (ifx % SE3_TILE_IF)) * PH + ph) * kTE] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 template <int P, int Q>
 static void launch_reg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* basis, int64_t E, int64_t tb, int n,
                        int k, int Ci, int F, int cpc, float* T) {
-  tbuild_reg_kernel<P, Q><<<grid, dim3(kTE, (P + 3) / 4), 0, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
+  constexpr int Fc = (P < Q) ? P : Q;
+  const size_t smem = (size_t)P * Q * Fc * kTE * sizeof(float);
+  cudaFuncSetAttribute(tbuild_reg_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tbuild_reg_kernel<P, Q><<<grid, dim3(kTE, kTbLanes), smem, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
 }
 
 }  // namespace se3
@@ -154,7 +163,7 @@ extern "C" int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* b
   SE3_REQUIRE(tile_begin >= 0 && tile_count > 0 && tile_begin + tile_count <= n_all, "se3_tbuild_fwd: tile range out of bounds");
   const int64_t n_mtiles = tile_count;
   // enough CTAs to fill the machine (148 SMs x a few CTAs) without shredding the channel loop
-  int slabs = (int)std::min<int64_t>(Ci, std::max<int64_t>(1, (148 * 8) / n_mtiles));
+  int slabs = (int)std::min<int64_t>(std::max(1, Ci / 16), std::max<int64_t>(1, (148 * 2 + n_mtiles - 1) / n_mtiles));
   const int ci_per_cta = (int)ceil_div(Ci, slabs);
   slabs = (int)ceil_div(Ci, ci_per_cta);
   dim3 grid((unsigned)n_mtiles, (unsigned)slabs);
