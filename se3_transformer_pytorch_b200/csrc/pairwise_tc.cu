@@ -22,11 +22,12 @@
 // 8 KiB of operands through the 128 B/clk shared-memory port, which (with the TMA writes and the epilogue's LDS)
 // made shared-memory bandwidth, not the tensor pipe, the limiter (profiles/r01_*).
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (warps 2,3 idle; the warpgroup
+// Warp roles (384 threads): warp 0 = W producer, warp 1 = TMEM owner + MMA issuer, warp 2 = T/bias producer (warp 3 idle; the warpgroup
 // gives its registers away with setmaxnreg), warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking
 // 16 of the 32 output channels, 208 registers each).
-// Pipelines: a ring of six 32 KiB W slots, one per (step, k-half) unit (producer -> MMA, released by tcgen05.commit),
-// two T/bias stages (producer -> epilogue), TMEM accumulator double buffer (MMA -> epilogue).
+// Pipelines: a ring of five 32 KiB W slots, one per (step, k-half) unit (warp 0 -> MMA, released by tcgen05.commit),
+// a ring of 3-4 T/bias stages (warp 2 -> epilogue; its own producer so T prefetch is not throttled by the W ring),
+// TMEM accumulator double buffer (MMA -> epilogue).
 // Thread-block clusters of CSZ CTAs (same channel block, CSZ consecutive edge tiles) share every W unit: each CTA
 // fetches 1/CSZ of it and multicasts it into all members' shared memory (cp.async.bulk ... .multicast::cluster), and
 // a W slot is recycled when every member's MMAs have retired (tcgen05.commit ... .multicast::cluster).  This cuts the
@@ -48,7 +49,8 @@ constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
 constexpr uint32_t kTmemCols = 512;              // 2 accumulator buffers x 128 columns + A hi/lo (64 + 64 columns)
 constexpr uint32_t kTmemAHi = 256, kTmemALo = 320;
 constexpr uint32_t kUnitBytes = 32768;           // one k-half of a W tile: [hi 16 KiB | lo 16 KiB]
-constexpr int kWSlots = 6;
+constexpr int kWSlots = 5;
+template <int PH> struct TStages { static constexpr int value = (PH == 1) ? 4 : 3; };   // T / bias ring depth (smem budget)
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -230,21 +232,22 @@ pairwise_tc_kernel(const TcParams prm) {
   const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, dbg = prm.dbg;
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;         // 4 (i,f) x PH x 128 edges x 16 B
+  constexpr int kTStages = TStages<PH>::value;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
   const uint32_t sW = base + TcSmem::W0;           // + slot * kUnitBytes
   const uint32_t sT = base + TcSmem::T0;           // + st * kTBytes
-  const uint32_t sBias = sT + 2 * kTBytes;         // + st * kBiasBytes
-  const uint32_t sBar = sBias + 2 * kBiasBytes;    // 8-byte barriers
+  const uint32_t sBias = sT + kTStages * kTBytes;  // + stage * kBiasBytes
+  const uint32_t sBar = sBias + kTStages * kBiasBytes;   // 8-byte barriers
   // barrier ids
   const uint32_t bar_a_full = sBar + 0;
   const uint32_t bar_w_full = sBar + 8;                       // [kWSlots]
   const uint32_t bar_w_empty = bar_w_full + 8 * kWSlots;      // [kWSlots]
-  const uint32_t bar_t_full = bar_w_empty + 8 * kWSlots;      // [2]
-  const uint32_t bar_t_empty = bar_t_full + 16;               // [2]
-  const uint32_t bar_tm_full = bar_t_empty + 16;              // [2]
+  const uint32_t bar_t_full = bar_w_empty + 8 * kWSlots;      // [kTStages]
+  const uint32_t bar_t_empty = bar_t_full + 8 * kTStages;     // [kTStages]
+  const uint32_t bar_tm_full = bar_t_empty + 8 * kTStages;    // [2]
   const uint32_t bar_tm_empty = bar_tm_full + 16;             // [2]
   const uint32_t s_tmem_slot = bar_tm_empty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
@@ -278,9 +281,11 @@ pairwise_tc_kernel(const TcParams prm) {
       mbar_init(bar_w_full + 8 * s, 1);
       mbar_init(bar_w_empty + 8 * s, CSZ);     // one tcgen05.commit arrival from every CTA of the cluster
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kTStages; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 8);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tm_full + 8 * s, 1);
       mbar_init(bar_tm_empty + 8 * s, 8);
     }
@@ -303,10 +308,7 @@ pairwise_tc_kernel(const TcParams prm) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kWTileBytes;
-      const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
       for (int s = 0; s < NIFB; ++s) {
-        const int st = s & 1;
-        const uint32_t ph = (uint32_t)(s >> 1) & 1u;
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh) {
           const int u = 2 * s + kh;
@@ -322,10 +324,20 @@ pairwise_tc_kernel(const TcParams prm) {
                         kShare, bar_w_full + 8 * slot, kMask);
           }
         }
-        mbar_wait(bar_t_empty + 8 * st, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_t_full + 8 * st, kTBytes + kBiasBytes);
-        bulk_g2s(sT + st * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * st);
-        bulk_g2s(sBias + st * kBiasBytes, wsrc + (size_t)s * kWTileBytes + kImgBytes, kBiasBytes, bar_t_full + 8 * st);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== T / bias producer =====================
+    if (lane == 0) {
+      const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kWTileBytes;
+      const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
+      for (int s = 0; s < NIFB; ++s) {
+        const int ts = s % kTStages;
+        const uint32_t tph = (uint32_t)(s / kTStages) & 1u;
+        mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
+        mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes + kBiasBytes);
+        bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * ts);
+        bulk_g2s(sBias + ts * kBiasBytes, wsrc + (size_t)s * kWTileBytes + kImgBytes, kBiasBytes, bar_t_full + 8 * ts);
       }
     }
   } else if (warp == 1) {
@@ -411,11 +423,13 @@ pairwise_tc_kernel(const TcParams prm) {
     for (int s = 0; s < NIFB; ++s) {
       const int st = s & 1;
       const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-      mbar_wait(bar_t_full + 8 * st, ph);
+      const int ts = s % kTStages;
+      const uint32_t tph = (uint32_t)(s / kTStages) & 1u;
+      mbar_wait(bar_t_full + 8 * ts, tph);
       mbar_wait(bar_tm_full + 8 * st, ph);
       tc_fence_after();
-      const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + st * kTBytes);
-      const float4* Bs = reinterpret_cast<const float4*>(base_ptr + (sBias - base) + st * kBiasBytes);
+      const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + ts * kTBytes);
+      const float4* Bs = reinterpret_cast<const float4*>(base_ptr + (sBias - base) + ts * kBiasBytes);
       const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + half * 16);
       // software pipeline inside the step: the accumulator columns of (i,f) slots 2,3 are in flight while slots 0,1
       // are contracted, so only one tcgen05.ld latency per step is exposed
@@ -469,7 +483,7 @@ pairwise_tc_kernel(const TcParams prm) {
       }
       // T / bias stage fully consumed
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_t_empty + 8 * st);
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
     }
     // write out[e, ob*32 + half*16 + (0..15), 0..P)
     const int64_t e = mt * SE3_TILE_E + el;
@@ -502,7 +516,7 @@ pairwise_tc_kernel(const TcParams prm) {
 template <int P>
 static size_t tc_smem_bytes() {
   constexpr int PH = (P + 3) / 4;
-  return 1024 + kWSlots * kUnitBytes + 2 * (PH * 8192u) + 2 * kBiasBytes + 192;
+  return 1024 + kWSlots * kUnitBytes + TStages<PH>::value * (PH * 8192u) + TStages<PH>::value * kBiasBytes + 256;
 }
 
 static int env_int(const char* name, int dflt) {

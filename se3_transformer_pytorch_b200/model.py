@@ -537,6 +537,13 @@ class SE3Transformer(nn.Module):
             m.pack_weights(free_master=free_master)
         return self
 
+    def graphed(self, feats, coors, mask=None, **fwd_kwargs):
+        """Capture one forward for these (static) input shapes in a CUDA graph and return a replayable callable
+        (see GraphedForward).  Small point clouds are launch bound (~100 kernels of a few microseconds each); replaying a
+        graph removes the per-launch host cost.  Not available with attend_sparse_neighbors / neighbor_mask (their
+        host-side `.item()` synchronisations, reference S:1208, 1253, cannot be captured)."""
+        return GraphedForward(self, feats, coors, mask, **fwd_kwargs)
+
     # ---- forward ----------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, feats, coors, mask=None, adj_mat=None, edges=None, return_type=None, return_pooled=False,
@@ -645,3 +652,41 @@ class SE3Transformer(nn.Module):
         if exists(return_type):
             return x[str(return_type)]
         return x
+
+
+class GraphedForward:
+    """CUDA-graph replay of SE3Transformer.forward for fixed shapes.  Inputs are copied into static device buffers
+    (host tensors are accepted: the copy is then the H2D transfer); the returned tensors are the graph's static outputs
+    and are overwritten by the next call."""
+
+    def __init__(self, model, feats, coors, mask=None, warmup=2, **fwd_kwargs):
+        assert not model.attend_sparse_neighbors and fwd_kwargs.get('neighbor_mask') is None, \
+            'graph capture needs a synchronisation-free forward'
+        dev = next(model.parameters()).device
+        self.model, self.kw = model, fwd_kwargs
+        clone = lambda t: t.to(dev).clone()
+        self.feats = {k: clone(v) for k, v in feats.items()} if isinstance(feats, dict) else clone(feats)
+        self.coors = clone(coors)
+        self.mask = None if mask is None else clone(mask)
+        self.static_kw = {k: (clone(v) if torch.is_tensor(v) else v) for k, v in fwd_kwargs.items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                    # builds weight images / tables outside the capture
+                model(self.feats, self.coors, self.mask, **self.static_kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model(self.feats, self.coors, self.mask, **self.static_kw)
+
+    def __call__(self, feats, coors, mask=None):
+        if isinstance(feats, dict):
+            for k, v in feats.items():
+                self.feats[k].copy_(v, non_blocking=True)
+        else:
+            self.feats.copy_(feats, non_blocking=True)
+        self.coors.copy_(coors, non_blocking=True)
+        if mask is not None:
+            self.mask.copy_(mask, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -112,6 +112,16 @@ CASES = [
 ]
 
 
+# BASELINE.json configs[2] at full size and configs[3] at batch 2 (outputs only; ~20 s and ~5 min of reference CPU time)
+BIG_CASES = [
+    dict(name='cfg3', ctor=dict(dim=64, depth=2, input_degrees=1, num_degrees=2, output_degrees=2, reduce_dim_out=True, num_neighbors=16),
+         b=2, n=256, fwd=dict(return_type=1), no_capture=True),
+    # configs[3] with batch 2 instead of 8: the reference needs ~8 GB per cloud here (band adjacency, 8 bonded neighbours)
+    dict(name='cfg4_b2', ctor=dict(dim=128, depth=2, num_degrees=3, num_edge_tokens=4, edge_dim=16, attend_sparse_neighbors=True,
+                                   num_neighbors=0, max_sparse_neighbors=8), b=2, n=512, edges='tokens', adj=4, no_capture=True),
+]
+
+
 def build_inputs(case):
     b, n = case['b'], case['n']
     name = case['name']
@@ -186,10 +196,11 @@ def run_case(case):
         for d, t in output.items():
             cap[f'conv_in/out/{d}'] = to_np(t)
 
-    hooks.append(model.conv_in.register_forward_pre_hook(conv_in_pre, with_kwargs=True))
-    hooks.append(model.conv_in.register_forward_hook(conv_in_post, with_kwargs=True))
+    if not case.get('no_capture'):
+        hooks.append(model.conv_in.register_forward_pre_hook(conv_in_pre, with_kwargs=True))
+        hooks.append(model.conv_in.register_forward_hook(conv_in_post, with_kwargs=True))
 
-    if not case['ctor'].get('use_egnn'):
+    if not case['ctor'].get('use_egnn') and not case.get('no_capture'):
         attn = model.net.blocks[0][0].attn
 
         def attn_pre(mod, args, kwargs):
@@ -257,9 +268,10 @@ if __name__ == '__main__':
         gen_sh_basis()
     if 'rot' in which:
         gen_equivariance_inputs()
-    if 'models' in which:
-        all_keys = {}
-        for case in CASES:
+    if 'models' in which or 'big' in which:
+        kpath = os.path.join(HERE, 'state_keys.json')
+        all_keys = json.load(open(kpath)) if os.path.exists(kpath) else {}
+        for case in (CASES if 'models' in which else []) + (BIG_CASES if 'big' in which else []):
             all_keys[case['name']] = run_case(case)
-        with open(os.path.join(HERE, 'state_keys.json'), 'w') as f:
+        with open(kpath, 'w') as f:
             json.dump(all_keys, f, indent=0, sort_keys=True)

@@ -9,6 +9,9 @@ MODEL_CASES = ['cfg1', 'deg4', 'af2', 'edges_sparse', 'ragged', 'tc_deg2', 'tc_d
                'linkeys', 'nullkv', 'noself', 'global', 'onehead', 'preconv_normout', 'tokens_pos', 'adjdeg', 'nbrmask',
                'contedges']
 
+# BASELINE.json configs[2] at full size, configs[3] at batch 2 (the reference needs ~8 GB of host RAM per cloud there)
+BIG_CASES = ['cfg3', 'cfg4_b2']
+
 
 def load_case(name):
     z = dict(np.load(os.path.join(GOLDEN, f'model_{name}.npz')))

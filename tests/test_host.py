@@ -6,12 +6,12 @@ import re
 import pytest
 import torch
 
-from helpers import MODEL_CASES, load_case, state_keys
+from helpers import MODEL_CASES, BIG_CASES, load_case, state_keys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('name', MODEL_CASES)
+@pytest.mark.parametrize('name', MODEL_CASES + BIG_CASES)
 def test_state_dict_layout_matches_reference(name):
     """Same parameter names and shapes as the reference: load_state_dict interchange."""
     from se3_transformer_pytorch_b200 import SE3Transformer
