@@ -11,8 +11,11 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
-LIB = os.path.join(PKG, 'libse3b200.so')
-STAMP = os.path.join(PKG, '.libse3b200.stamp')
+# tuning experiments: SE3B200_LIB_TAG=_x SE3B200_NVCC_DEFS="-DSE3_W_SLOTS=6 ..." build/load a side-by-side variant
+TAG = os.environ.get('SE3B200_LIB_TAG', '')
+EXTRA_DEFS = os.environ.get('SE3B200_NVCC_DEFS', '').split()
+LIB = os.path.join(PKG, f'libse3b200{TAG}.so')
+STAMP = os.path.join(PKG, f'.libse3b200{TAG}.stamp')
 SOURCES = ['api.cu', 'graph.cu', 'basis.cu', 'radial.cu', 'tbuild.cu', 'pairwise_simt.cu', 'pairwise_tc.cu', 'attention.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
@@ -31,7 +34,7 @@ def _digest():
     for f in files:
         with open(f, 'rb') as fh:
             h.update(f.encode() + b'\0' + fh.read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update(' '.join(NVCC_FLAGS + EXTRA_DEFS).encode())
     return h.hexdigest()
 
 
@@ -47,10 +50,10 @@ def build(force=False, verbose=False):
     if not force and is_current():
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
+    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + EXTRA_DEFS
     objs = []
     procs = []
-    objdir = os.path.join(PKG, 'build')
+    objdir = os.path.join(PKG, 'build' + TAG)
     os.makedirs(objdir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))

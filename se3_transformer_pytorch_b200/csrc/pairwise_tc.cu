@@ -49,8 +49,17 @@ constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
 constexpr uint32_t kTmemCols = 512;              // 2 accumulator buffers x 128 columns + A hi/lo (64 + 64 columns)
 constexpr uint32_t kTmemAHi = 256, kTmemALo = 320;
 constexpr uint32_t kUnitBytes = 32768;           // one k-half of a W tile: [hi 16 KiB | lo 16 KiB]
-constexpr int kWSlots = 5;
-template <int PH> struct TStages { static constexpr int value = (PH == 1) ? 4 : 3; };   // T / bias ring depth (smem budget)
+#ifndef SE3_W_SLOTS
+#define SE3_W_SLOTS 5
+#endif
+#ifndef SE3_T_STAGES_P1
+#define SE3_T_STAGES_P1 4
+#endif
+#ifndef SE3_T_STAGES_P2
+#define SE3_T_STAGES_P2 3
+#endif
+constexpr int kWSlots = SE3_W_SLOTS;
+template <int PH> struct TStages { static constexpr int value = (PH == 1) ? SE3_T_STAGES_P1 : SE3_T_STAGES_P2; };   // T / bias ring depth (smem budget)
 
 
 // ---------------------------------------------------------------------------------------------------------
