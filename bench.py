@@ -342,7 +342,7 @@ def run_ours(args, wl, rank, local_rank, world):
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                     'frac': ach / peaks['bf16_sustained'], 'traffic': traffic, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
                     'avg_launch_ms': d['ms'] / d['launches'], 'share_of_step': d['ms'] / ms_res,
-                    'note': 'achieved = algorithmic FLOPs (2*128 + 2*(2lo+1) per R element); the kernel issues 3 bf16 MMA passes per '
+                    'note': 'achieved = algorithmic FLOPs (2*128 + 2*(2lo+1) per R element); the kernel issues 3 fp16 MMA passes per '
                             'algorithmic GEMM FLOP for fp32 parity, so tensor-pipe work is ~3x this figure'}
         else:
             ach = d['bytes'] / (d['ms'] / 1e3) / 1e9

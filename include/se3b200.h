@@ -20,7 +20,7 @@
  *   - return value 0 = success; otherwise a negative SE3_E* code and se3_last_error() (HOST string,
  *     thread-local) describes the failure.  No CPU fallback exists.
  *   - fp32 arithmetic throughout; the tensor-core kernel evaluates its one dense contraction as a
- *     3-pass bf16 split (hi*hi + lo*hi + hi*lo, fp32 accumulate), error ~1e-6 relative.
+ *     3-pass fp16 split (x = hi + lo, 22 mantissa bits; hi*hi + lo*hi + hi*lo, fp32 accumulate), error < 1e-6 relative.
  */
 #ifndef SE3B200_H
 #define SE3B200_H
@@ -86,12 +86,12 @@ int se3_pairwise_simt_fwd(const float* g, const float* W3, const float* b3, cons
                           int64_t E, int Co, int Ci, int F, int P, int accumulate, float* out, void* stream);
 
 /* Pack RadialFunc.net.6 weight/bias into the tensor-core operand image (once per weight update).
- * bytes needed: se3_w3_image_bytes(Co, Ci, F).  Requires Co % 32 == 0. */
+ * bytes needed: se3_w3_image_bytes(Co, Ci, F).  Requires Co % 32 == 0 and |W3| < 6e4 (fp16 hi/lo split). */
 int64_t se3_w3_image_bytes(int Co, int Ci, int F);
 int se3_pack_w3(const float* W3, const float* b3, int Co, int Ci, int F, void* image, void* stream);
 
 /* Same contraction as se3_pairwise_simt_fwd on the tcgen05 tensor cores (sm_100a only): g [E,128] fp32 from
- * se3_radial_trunk_fwd (one pair's slice; split to bf16 hi/lo into tensor memory inside the kernel), w_img from
+ * se3_radial_trunk_fwd (one pair's slice; split to fp16 hi/lo into tensor memory inside the kernel), w_img from
  * se3_pack_w3, T from se3_tbuild_fwd. */
 int se3_pairwise_tc_fwd(const float* g, const void* w_img, const float* T,
                         int64_t E, int Co, int Ci, int F, int P, int accumulate, float* out, void* stream);

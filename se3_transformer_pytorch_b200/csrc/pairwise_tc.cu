@@ -6,8 +6,11 @@
 // mat-vec and sum over degree_in of ConvSE3.forward (S:251-254), in the factored form of SURVEY.md A.4.
 //
 // The only dense contraction, R = g . W3^T  (M = 128 edges, N = 128 (o,i,f) columns, K = 128), runs on the 5th-gen
-// tensor cores (tcgen05.mma, cta_group::1, M128 N128 K16, bf16 x bf16 -> fp32 in TMEM).  fp32 parity is kept with a
-// 3-pass bf16 split:  g = g_hi + g_lo, W = W_hi + W_lo,  R ~= g_hi W_hi + g_lo W_hi + g_hi W_lo  (24 MMAs per tile).
+// tensor cores (tcgen05.mma, cta_group::1, M128 N128 K16, 16-bit x 16-bit -> fp32 in TMEM).  fp32 parity is kept with a
+// 3-pass fp16 split:  g = g_hi + g_lo, W = W_hi + W_lo with hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits per
+// operand (a bf16 pair carries only 16 and cost 10x the error; mixing bf16 hi with fp16 lo in one MMA is an illegal
+// instruction on sm_100a).  R ~= g_hi W_hi + g_lo W_hi + g_hi W_lo  (24 MMAs per tile).  fp16 range: the host only
+// selects this kernel when |W3| and the LayerNorm-bounded |g| stay below 6e4 (else the fp32 SIMT kernel runs).
 // R never leaves the SM: epilogue warps read the accumulator tile with tcgen05.ld, add the bias and contract it with the
 // per-edge T block (packed fp32x2 FMAs), keeping out[e, 32 o, P] in registers across the whole (i,f) loop.
 //
@@ -17,7 +20,7 @@
 // filled by 1-D TMA bulk copies (cp.async.bulk, completion on mbarriers) with no tensor maps.
 //
 // The A operand (the 128 x 128 tile of g, stationary for the whole CTA) lives in TENSOR MEMORY, not shared memory:
-// four epilogue warps read the fp32 rows of g, split them into bf16 hi/lo and tcgen05.st them into 128 TMEM columns;
+// four epilogue warps read the fp32 rows of g, split them into fp16 hi/lo and tcgen05.st them into 128 TMEM columns;
 // every MMA is the .ts form (A from TMEM, B from smem).  Measured reason: with A in smem each M128 N128 K16 MMA pulls
 // 8 KiB of operands through the 128 B/clk shared-memory port, which (with the TMA writes and the epilogue's LDS)
 // made shared-memory bandwidth, not the tensor pipe, the limiter (profiles/r01_*).
@@ -36,6 +39,7 @@
 // the CTAs resident together share T tiles and W tiles through L2.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <algorithm>
 
@@ -43,7 +47,7 @@ namespace se3 {
 
 constexpr int kTcThreads = 384;                // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
 constexpr uint32_t kImgBytes = 65536;            // one 128x128 hi+lo operand image (4 sub-tiles of 16 KiB)
-constexpr uint32_t kSubBytes = 16384;            // 128 rows x 64 bf16, SW128
+constexpr uint32_t kSubBytes = 16384;            // 128 rows x 64 fp16, SW128
 constexpr uint32_t kBiasBytes = 512;             // 128 fp32
 constexpr uint32_t kWTileBytes = kImgBytes + kBiasBytes;
 constexpr uint32_t kTmemCols = 512;              // 2 accumulator buffers x 128 columns + A hi/lo (64 + 64 columns)
@@ -118,7 +122,7 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -126,7 +130,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -170,7 +174,7 @@ __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigne
   return d;
 }
 
-// UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart)
+// UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 halves = 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
@@ -180,8 +184,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D fp32, A/B 16-bit (format 0 = fp16, 1 = bf16), both K-major, M = 128, N = 128
+constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+}
+constexpr uint32_t kIdescF16 = make_idesc(0, 0);    // fp16 x fp16 (operands of one tcgen05.mma must share the format)
 
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
   const int kh = k >> 6, kk = k & 63;
@@ -201,12 +208,12 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
     const int r = t >> 7, k = t & 127;
     const int o = ob * SE3_TILE_O + (r & 31), ifx = ifb * SE3_TILE_IF + (r >> 5);
     const float w = (ifx < CiF) ? W3[((size_t)o * CiF + ifx) * SE3_RADIAL_MID + k] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    // W tile image: [k-half 0: hi | lo][k-half 1: hi | lo], each sub-tile 128 rows x 64 bf16, SW128
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    // W tile image: [k-half 0: hi | lo][k-half 1: hi | lo], each sub-tile 128 rows x 64 fp16, SW128
     const uint32_t off = (uint32_t)(k >> 6) * kUnitBytes + sw128_off(r, k & 63);
-    *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(dst + kSubBytes + off) = lo;
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + kSubBytes + off) = lo;
     if (k == 0) reinterpret_cast<float*>(dst + kImgBytes)[r] = (ifx < CiF) ? b3[(size_t)o * CiF + ifx] : 0.f;
   }
 }
@@ -376,7 +383,7 @@ pairwise_tc_kernel(const TcParams prm) {
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
-              if (!(dbg & 2)) tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kIdesc, accum);
+              if (!(dbg & 2)) tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kIdescF16, accum);
               accum = 1;
             }
           }
@@ -395,7 +402,7 @@ pairwise_tc_kernel(const TcParams prm) {
     const int el = q * 32 + lane;              // edge row inside the tile
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
     if (half == 0) {
-      // ---- A operand: this thread's edge row of g (fp32) -> bf16 hi/lo pairs -> tensor memory
+      // ---- A operand: this thread's edge row of g (fp32) -> fp16 hi / lo pairs -> tensor memory
       const int64_t eg = mt * SE3_TILE_E + el;
       const float4* grow = reinterpret_cast<const float4*>(g + (size_t)(eg < E ? eg : 0) * SE3_RADIAL_MID);
       const bool live = eg < E;
@@ -408,11 +415,11 @@ pairwise_tc_kernel(const TcParams prm) {
           const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(xs[2 * h2]), h1 = __float2bfloat16_rn(xs[2 * h2 + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(xs[2 * h2] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(xs[2 * h2 + 1] - __bfloat162float(h1));
-            hi[v * 2 + h2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[v * 2 + h2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const __half h0 = __float2half_rn(xs[2 * h2]), h1 = __float2half_rn(xs[2 * h2 + 1]);
+            const __half l0 = __float2half_rn(xs[2 * h2] - __half2float(h0));
+            const __half l1 = __float2half_rn(xs[2 * h2 + 1] - __half2float(h1));
+            hi[v * 2 + h2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[v * 2 + h2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
         }
         tmem_st16(tmem_base + t_lane + kTmemAHi + (uint32_t)(c * 16), hi);

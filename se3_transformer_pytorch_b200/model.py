@@ -197,8 +197,12 @@ class ConvSE3(nn.Module):
             for di, do in self.pairs:
                 pc = self.kernel_unary[f'({di},{do})']
                 if ops.tc_supported(dev, pc.nc_out, pc.d_out):
-                    lin = pc.rp.net['6']
-                    images[(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
+                    lin, ln = pc.rp.net['6'], pc.rp.net['4']
+                    # fp16 range guard of the split-precision operands: |g| <= sqrt(127) max|ln.w| + max|ln.b| after
+                    # LayerNorm + GELU; outside it the pair runs on the fp32 SIMT kernel
+                    g_bound = 11.3 * float(ln.weight.abs().max()) + float(ln.bias.abs().max())
+                    if float(lin.weight.abs().max()) < 6.0e4 and g_bound < 6.0e4:
+                        images[(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
         self._packed = dict(version=ver, trunk=trunk, images=images)
         return self._packed
 
