@@ -12,6 +12,7 @@
  *                                                                                               se3_pairwise_{simt,tc}_fwd
  *   masked_mean pooling of ConvSE3                     utils.py:72-80, S:256-257             -> se3_pool_fwd
  *   AttentionSE3.forward logits/softmax/aggregate      se3_transformer_pytorch.py:476-517    -> se3_attn_fwd
+ *   NormSE3.forward (next to the hot path)  se3_transformer_pytorch.py:130-152    -> se3_norm_fwd
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to a contiguous row-major buffer unless marked HOST;
@@ -102,6 +103,10 @@ int se3_pairwise_tc_debug(const float* g, const void* w_img, const float* T, int
 
 /* Masked mean over the neighbour axis (utils.py:72-80): x [B, K, C] , mask [B, K] (NULL = plain mean) -> out [B, C]. */
 int se3_pool_fwd(const float* x, const uint8_t* mask, int64_t B, int K, int64_t C, float* out, void* stream);
+
+/* NormSE3 (S:97-152, non-gated): x, out [rows = b*n*C, M]; norm = max(||x[r,:]||, eps);
+ * out[r,:] = f(norm * scale[r % C]) * x[r,:] / norm with f = exact-erf GELU (use_gelu != 0) or identity. */
+int se3_norm_fwd(const float* x, const float* scale, int64_t rows, int C, int M, float eps, int use_gelu, float* out, void* stream);
 
 /* Attention for one degree (S:476-517): for every node i and head h
  *   keys/values along j = [global (G) | null (0/1) | self (0/1) | K neighbours]  (prepend order of S:485,499,505)

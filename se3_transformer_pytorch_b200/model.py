@@ -103,6 +103,12 @@ class NormSE3(nn.Module):
     def forward(self, features):
         out = {}
         for degree, t in features.items():
+            pd = self.transform[degree]
+            fused = 'scale' in pd and t.is_cuda and t.dtype == torch.float32 and isinstance(self.nonlin, (nn.GELU, nn.Identity)) \
+                and not (isinstance(self.nonlin, nn.GELU) and self.nonlin.approximate != 'none')
+            if fused:                                    # one fused kernel (libse3b200: se3_norm_fwd)
+                out[degree] = ops.norm_se3(t, pd['scale'], self.eps, isinstance(self.nonlin, nn.GELU))
+                continue
             norm = t.norm(dim=-1, keepdim=True).clamp(min=self.eps)
             phase = t / norm
             pd = self.transform[degree]

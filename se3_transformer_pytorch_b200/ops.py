@@ -33,6 +33,7 @@ _SIGNATURES = {
     'se3_pairwise_tc_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
     'se3_pairwise_tc_debug': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -362,4 +363,15 @@ def attention(q, k, v, *, heads, dim_head, scale, nmask=None, k_idx=None, self_k
     with torch.cuda.device(q.device), _timed('attention', flops=4 * b * n * J * heads * dim_head * M, nbytes=nbytes):
         _check(lib().se3_attn_fwd(_p(q), _p(k), _p(v), _p(ki), _p(self_k), _p(self_v), _p(null_k), _p(null_v), _p(global_k),
                                   _p(global_v), G, _p(nm), b, n, K, heads, dim_head, M, kv_heads, float(scale), _p(out), _stream()))
+    return out
+
+
+def norm_se3(x, scale, eps, use_gelu):
+    """NormSE3 with a per-channel scale (reference S:130-152): x [b,n,C,M] -> same shape."""
+    _require_cuda(x, scale)
+    x = _f32(x)
+    C, M = x.shape[-2], x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device), _timed('norm', nbytes=8 * x.numel()):
+        _check(lib().se3_norm_fwd(_p(x), _p(_f32(scale).reshape(-1)), x.numel() // M, C, M, float(eps), int(use_gelu), _p(out), _stream()))
     return out

@@ -306,6 +306,20 @@ def test_attention(M, Dh, H, K, opts):
     assert rel_err(got, ref) < 5e-6
 
 
+@pytest.mark.parametrize('M,gelu', [(1, True), (3, True), (7, True), (5, False)])
+def test_norm_se3(M, gelu):
+    from se3_transformer_pytorch_b200 import ops
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((2, 9, 12, M)).astype(np.float32)
+    x[0, 0, 0] = 0.0                                            # zero vector: norm clamps to eps, output 0
+    scale = (1 + 0.1 * rng.standard_normal((1, 1, 12))).astype(np.float32)
+    P = {'transform.0.scale': scale.astype(np.float64)}
+    ref = O.norm_se3({'0': x.astype(np.float64)}, P, '', nonlin=O.gelu if gelu else (lambda t: t))['0']
+    got = ops.norm_se3(cu(x), cu(scale), 1e-12, gelu).cpu().numpy()
+    assert rel_err(got, ref) < 2e-6
+    assert np.all(got[0, 0, 0] == 0)
+
+
 def test_errors_are_loud():
     from se3_transformer_pytorch_b200 import ops
     with pytest.raises(RuntimeError, match='k must be'):
