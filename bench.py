@@ -236,7 +236,9 @@ def run_ours(args, wl, rank, local_rank, world):
     with torch.device(dev):
         model = SE3Transformer(**wl['ctor'])
     model.eval()
-    model.pack_weights(free_master=True)         # tensor-core operand images; fp32 masters of net.6 released (inference)
+    lowrank = ops.lowrank_enabled(wl['b'] * wl['n'] * min(wl['ctor']['num_neighbors'], wl['n'] - 1))
+    if not lowrank:
+        model.pack_weights(free_master=True)     # direct-kernel operand images; fp32 masters of net.6 released (inference)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     b, n, dim = wl['b'], wl['n'], wl['ctor']['dim']
@@ -367,7 +369,7 @@ def run_ours(args, wl, rank, local_rank, world):
         'data': 'synthetic',
         'config': {'workload': args.workload, **wl['ctor'], 'batch_per_gpu': b, 'global_batch': b * world, 'n_points': n,
                    'parallelism': f'dp{world} (batch sharded, replicated weights, one all-gather of outputs)',
-                   'cache': 'inputs larger than L2: every step streams the 77 GB weight image', 'random_init': True, 'cuda_graph': bool(args.cuda_graph),
+                   'cache': 'inputs larger than L2: every step streams the 77 GB weight image', 'random_init': True, 'cuda_graph': bool(args.cuda_graph), 'lowrank_radial': bool(lowrank),
                    'flops_per_cloud': forward_flops(wl) / b, 'model_build_s': t_build},
         'e2e': {'value': e2e, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,

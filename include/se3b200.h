@@ -101,6 +101,17 @@ int se3_pairwise_tc_fwd(const float* g, const void* w_img, const float* T,
 int se3_pairwise_tc_debug(const float* g, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
                           int P, int accumulate, float* out, float* dumpR, void* stream);
 
+/* Low-rank radial path.  When the trunk outputs of a pair, G [E,128], factor as G ~= U V^T with small rank r (distance-only
+ * radial functions: r ~ 16), the host passes
+ *   U  [E, 64] fp32: columns 0..r-1 = G V, column r = 1 (bias slot), remaining columns 0;
+ *   Fp [Co*Ci*F, Kp] fp32: columns 0..r-1 = W3 V, column r = b3, remaining 0;  Kp = 16*ceil((r+1)/16) <= 64
+ * se3_pack_lowrank images Fp for the tensor cores (se3_lowrank_image_bytes bytes) and se3_pairwise_lr_fwd evaluates the
+ * same contraction as se3_pairwise_tc_fwd with K = Kp instead of 128 (bias folded into the GEMM). */
+int64_t se3_lowrank_image_bytes(int Co, int Ci, int F);
+int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, void* image, void* stream);
+int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                        int Kp, int accumulate, float* out, void* stream);
+
 /* Masked mean over the neighbour axis (utils.py:72-80): x [B, K, C] , mask [B, K] (NULL = plain mean) -> out [B, C]. */
 int se3_pool_fwd(const float* x, const uint8_t* mask, int64_t B, int K, int64_t C, float* out, void* stream);
 

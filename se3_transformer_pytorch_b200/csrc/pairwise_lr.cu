@@ -1,0 +1,405 @@
+// K4 (tensor cores, low-rank radial path): the fused pairwise kernel when the radial-trunk outputs of a pair,
+// G = [g(e)]_e in R^{E x 128}, are numerically low rank.
+//
+// For distance-only radial functions (no per-edge features besides r_ij: BASELINE cfg1/2/3/5) every row of G is a point
+// on a smooth one-parameter curve g(|r_ij|), and G has numerical rank ~16 to 1e-7 (measured).
+// The host factors  G ~= U V^T  (U: E x r, V: 128 x r orthonormal, residual verified every forward) and folds V into the
+// last radial layer:
+//     R[e,(o,i,f)] = W3[(o,i,f),:] . g[e,:] + b3  =  [U[e,:], 1] . [F'[(o,i,f),:], b3]      with F' = W3 V  (N x r)
+// so the dense contraction has K = r+1 <= 64 instead of 128 and the bias rides along as one more K column.  Everything
+// downstream is unchanged:   out[e,o,p] (+)= sum_{i,f} R[e,o,i,f] * T[e,i,f,p]   (reference S:294-299, 326-343, 251-254).
+//
+// With the GEMM 4-8x cheaper the kernel is bound by its epilogue (P fp32 FMAs per R element), so this variant is built
+// around the epilogue: 16 epilogue warps (one per TMEM lane quarter x 8-channel slice), 4 per SM sub-partition, each
+// keeping out[e, 8 o, P] in registers, packed fp32x2 FMAs only (no bias add), T values from conflict-free LDS.128.
+//
+// One CTA = 128 edges x 32 channels, loops over ceil(C_in*f/4) steps; per step one N=128 accumulator tile (column =
+// if_local*32 + o_local), 3 passes (fp16 hi/lo split) x Kp/16 tcgen05.mma with A (= U tile, hi/lo) resident in tensor
+// memory and B tiles (F' image, [hi | lo] x 128 rows x 64 K, SW128) streamed by TMA bulk copies, multicast over a
+// 2-CTA cluster.  640 threads: warp 0 W producer, warp 1 TMEM owner + MMA issuer, warp 2 T producer, warps 4-19 epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
+#include <algorithm>
+
+namespace se3 {
+
+constexpr int kLrThreads = 640;
+constexpr uint32_t kLrUnitBytes = 2 * kSubBytes;   // one W tile: [hi 16 KiB | lo 16 KiB], K padded to 64
+constexpr int kLrWSlots = 4;
+constexpr int kLrTStages = 4;
+constexpr uint32_t kLrTmemCols = 512;              // 2 accumulator buffers (256) + A hi (32) + A lo (32)
+constexpr uint32_t kLrAHi = 256, kLrALo = 288;
+constexpr uint32_t kLrIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // fp16 x fp16 -> fp32, M128 N128
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+// F'' image packer: Fp fp32 [Co*Ci*F, Kp] (columns 0..r-1 = W3 V, column r = b3, rest 0) -> per (32-channel block,
+// 4-(i,f) block) tile [hi 128 x 64 | lo 128 x 64] fp16, SW128, row = if_local*32 + o_local
+__global__ void pack_lr_kernel(const float* __restrict__ Fp, int Co, int CiF, int NIFB, int Kp, uint8_t* __restrict__ img) {
+  const int64_t tile = blockIdx.x;
+  const int ob = (int)(tile / NIFB), ifb = (int)(tile % NIFB);
+  uint8_t* dst = img + (size_t)tile * kLrUnitBytes;
+  for (int t = threadIdx.x; t < 128 * 64; t += blockDim.x) {
+    const int r = t >> 6, k = t & 63;
+    const int o = ob * SE3_TILE_O + (r & 31), ifx = ifb * SE3_TILE_IF + (r >> 5);
+    const float w = (ifx < CiF && k < Kp) ? Fp[((size_t)o * CiF + ifx) * Kp + k] : 0.f;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    const uint32_t off = sw128_off(r, k);
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + kSubBytes + off) = lo;
+  }
+}
+
+struct LrParams {
+  const float* U;          // [E, 64] fp32: columns 0..r-1 = G V, column r = 1, rest 0
+  const uint8_t* w_img;
+  const float* T;
+  float* out;
+  int64_t E;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o;
+};
+
+template <int P, int CSZ>
+__global__ void __launch_bounds__(kLrThreads, 1)
+pairwise_lr_kernel(const LrParams prm) {
+  const float* __restrict__ U = prm.U;
+  const uint8_t* __restrict__ w_img = prm.w_img;
+  const float* __restrict__ T = prm.T;
+  float* __restrict__ out = prm.out;
+  const int64_t E = prm.E;
+  const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, nk16 = prm.nk16;
+  constexpr int PH = (P + 3) / 4;
+  constexpr uint32_t kTBytes = PH * 8192u;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sW = base;                                   // + slot * kLrUnitBytes
+  const uint32_t sT = sW + kLrWSlots * kLrUnitBytes;          // + stage * kTBytes
+  const uint32_t sBar = sT + kLrTStages * kTBytes;
+  const uint32_t bar_a_full = sBar + 0;
+  const uint32_t bar_w_full = sBar + 8;
+  const uint32_t bar_w_empty = bar_w_full + 8 * kLrWSlots;
+  const uint32_t bar_t_full = bar_w_empty + 8 * kLrWSlots;
+  const uint32_t bar_t_empty = bar_t_full + 8 * kLrTStages;
+  const uint32_t bar_tm_full = bar_t_empty + 8 * kLrTStages;  // [2]
+  const uint32_t bar_tm_empty = bar_tm_full + 16;             // [2]
+  const uint32_t s_tmem_slot = bar_tm_empty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = (CSZ > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
+  int64_t mt;
+  int ob;
+  bool active;
+  {
+    const int64_t cid = blockIdx.x / CSZ;
+    const int n_mg = (n_mt + CSZ - 1) / CSZ;
+    const int64_t per_band = (int64_t)prm.band_m * n_ob;
+    const int64_t band = cid / per_band;
+    const int64_t r = cid - band * per_band;
+    const int64_t g0 = band * prm.band_m;
+    const int rows = (int)min((int64_t)prm.band_m, (int64_t)n_mg - g0);
+    const int go = (n_ob % prm.band_o == 0) ? prm.band_o : 1;
+    const int64_t chunk = r / ((int64_t)rows * go);
+    const int64_t rr = r - chunk * rows * go;
+    ob = (int)(chunk * go + rr % go);
+    mt = (g0 + rr / go) * CSZ + crank;
+    active = mt < n_mt;
+    if (!active) mt = n_mt - 1;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 4);
+    for (int s = 0; s < kLrWSlots; ++s) {
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, CSZ);
+    }
+    for (int s = 0; s < kLrTStages; ++s) {
+      mbar_init(bar_t_full + 8 * s, 1);
+      mbar_init(bar_t_empty + 8 * s, 16);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tm_full + 8 * s, 1);
+      mbar_init(bar_tm_empty + 8 * s, 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kLrTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CSZ > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== W producer =====================
+      if (lane == 0) {
+        const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kLrUnitBytes;
+        constexpr uint32_t kShare = kLrUnitBytes / CSZ;
+        for (int s = 0; s < NIFB; ++s) {
+          const int slot = s % kLrWSlots;
+          const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
+          mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
+          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kLrUnitBytes);
+          if (CSZ == 1) {
+            bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)s * kLrUnitBytes, kLrUnitBytes, bar_w_full + 8 * slot);
+          } else {
+            bulk_g2s_mc(sW + slot * kLrUnitBytes + crank * kShare, wsrc + (size_t)s * kLrUnitBytes + crank * kShare, kShare,
+                        bar_w_full + 8 * slot, kMask);
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ===================== T producer =====================
+      if (lane == 0) {
+        const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
+        for (int s = 0; s < NIFB; ++s) {
+          const int ts = s % kLrTStages;
+          const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
+          mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
+          mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes);
+          bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * ts);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        mbar_wait(bar_a_full, 0);
+        tc_fence_after();
+        for (int s = 0; s < NIFB; ++s) {
+          const int st = s & 1;
+          const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+          const int slot = s % kLrWSlots;
+          const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
+          mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
+          mbar_wait(bar_w_full + 8 * slot, wph);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
+          const uint32_t wbase = sW + slot * kLrUnitBytes;
+          uint32_t accum = 0;
+          // pass 0: U_hi x F_hi   pass 1: U_lo x F_hi   pass 2: U_hi x F_lo
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_tmem = tmem_base + ((pass == 1) ? kLrALo : kLrAHi);
+            const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
+            for (int k16 = 0; k16 < nk16; ++k16) {
+              const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
+              tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
+              accum = 1;
+            }
+          }
+          if (CSZ == 1) tc_commit(bar_w_empty + 8 * slot);
+          else tc_commit_mc(bar_w_empty + 8 * slot, kMask);
+          tc_commit(bar_tm_full + 8 * st);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int oq = (warp - 4) >> 2;            // which 8 of the 32 output channels
+    const int el = q * 32 + lane;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    if (oq == 0) {
+      // ---- A operand: this thread's row of U (fp32, 64 columns) -> fp16 hi / lo pairs -> tensor memory
+      const int64_t eg = mt * SE3_TILE_E + el;
+      const bool live = eg < E;
+      const float4* urow = reinterpret_cast<const float4*>(U + (size_t)(live ? eg : 0) * 64);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {            // 32 k values -> 16 packed columns per chunk
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 x = live ? urow[c * 8 + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const __half h0 = __float2half_rn(xs[2 * h2]), h1 = __float2half_rn(xs[2 * h2 + 1]);
+            const __half l0 = __float2half_rn(xs[2 * h2] - __half2float(h0));
+            const __half l1 = __float2half_rn(xs[2 * h2 + 1] - __half2float(h1));
+            hi[v * 2 + h2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[v * 2 + h2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+        }
+        tmem_st16(tmem_base + t_lane + kLrAHi + (uint32_t)(c * 16), hi);
+        tmem_st16(tmem_base + t_lane + kLrALo + (uint32_t)(c * 16), lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+    }
+    unsigned long long acc[4][P];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[a][p] = 0ull;
+
+    for (int s = 0; s < NIFB; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+      const int ts = s % kLrTStages;
+      const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
+      mbar_wait(bar_tm_full + 8 * st, ph);
+      tc_fence_after();
+      const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + oq * 8);
+      uint32_t r[4][8];
+#pragma unroll
+      for (int ifl = 0; ifl < 4; ++ifl) tmem_ld8(tcol + (uint32_t)(ifl * 32), r[ifl]);
+      mbar_wait(bar_t_full + 8 * ts, tph);
+      const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + ts * kTBytes);
+      tmem_ld_wait();
+      // all accumulator reads of this step have landed in registers: give the buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
+#pragma unroll
+      for (int ifl = 0; ifl < 4; ++ifl) {
+        float tv[PH * 4];
+#pragma unroll
+        for (int h4 = 0; h4 < PH; ++h4) {
+          const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
+          tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const unsigned long long t2 = pack2(tv[p], tv[p]);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const unsigned long long R2 = pack2(__uint_as_float(r[ifl][2 * a]), __uint_as_float(r[ifl][2 * a + 1]));
+            acc[a][p] = fma2(R2, t2, acc[a][p]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
+    }
+    // write out[e, ob*32 + oq*8 + (0..7), 0..P)
+    const int64_t e = mt * SE3_TILE_E + el;
+    if (active && e < E) {
+      float* dst = out + ((size_t)e * Co + (size_t)ob * SE3_TILE_O + oq * 8) * P;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          float v0, v1;
+          unpack2(acc[a][p], v0, v1);
+          float* d0 = dst + (2 * a) * P + p;
+          float* d1 = dst + (2 * a + 1) * P + p;
+          if (accumulate) { v0 += *d0; v1 += *d1; }
+          *d0 = v0;
+          *d1 = v1;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CSZ > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kLrTmemCols) : "memory");
+  }
+}
+
+template <int P>
+static size_t lr_smem_bytes() {
+  constexpr int PH = (P + 3) / 4;
+  return 1024 + kLrWSlots * kLrUnitBytes + kLrTStages * (PH * 8192u) + 256;
+}
+
+template <int P, int CSZ>
+static int launch_lr(const LrParams& prm, cudaStream_t s) {
+  const size_t smem = lr_smem_bytes<P>();
+  auto kern = pairwise_lr_kernel<P, CSZ>;
+  SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_mg = (prm.n_mt + CSZ - 1) / CSZ;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((int64_t)n_mg * prm.n_ob * CSZ));
+  cfg.blockDim = dim3(kLrThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSZ;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SE3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prm));
+  return SE3_OK;
+}
+
+static int lr_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace se3
+
+extern "C" int64_t se3_lowrank_image_bytes(int Co, int Ci, int F) {
+  if (Co <= 0 || Ci <= 0 || F <= 0 || Co % SE3_TILE_O != 0) return -1;
+  const int64_t NIFB = se3::ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  return (int64_t)(Co / SE3_TILE_O) * NIFB * se3::kLrUnitBytes;
+}
+
+extern "C" int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, void* image, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(Co > 0 && Ci > 0 && F > 0 && Co % SE3_TILE_O == 0, "se3_pack_lowrank: Co must be a positive multiple of %d", SE3_TILE_O);
+  SE3_REQUIRE(Kp >= 16 && Kp <= 64 && Kp % 16 == 0, "se3_pack_lowrank: Kp=%d must be 16, 32, 48 or 64", Kp);
+  const int CiF = Ci * F;
+  const int NIFB = (int)ceil_div(CiF, SE3_TILE_IF);
+  const int64_t tiles = (int64_t)(Co / SE3_TILE_O) * NIFB;
+  SE3_REQUIRE(tiles < 2147483647ll, "se3_pack_lowrank: too many tiles");
+  pack_lr_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(Fp, Co, CiF, NIFB, Kp, reinterpret_cast<uint8_t*>(image));
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                                   int Kp, int accumulate, float* out, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_lr_fwd: bad sizes");
+  SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_lr_fwd: Co=%d must be a multiple of %d", Co, SE3_TILE_O);
+  SE3_REQUIRE(P == 1 || P == 3 || P == 5 || P == 7, "se3_pairwise_lr_fwd: P=%d unsupported (degree_out <= 3)", P);
+  SE3_REQUIRE(Kp >= 16 && Kp <= 64 && Kp % 16 == 0, "se3_pairwise_lr_fwd: Kp=%d must be 16, 32, 48 or 64", Kp);
+  SE3_REQUIRE((ceil_div(E, SE3_TILE_E) + 4) * (Co / SE3_TILE_O) < 2147483647ll, "se3_pairwise_lr_fwd: grid too large");
+  LrParams prm;
+  prm.U = U;
+  prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  prm.T = T;
+  prm.out = out;
+  prm.E = E;
+  prm.Co = Co;
+  prm.NIFB = (int)ceil_div((int64_t)Ci * F, SE3_TILE_IF);
+  prm.n_mt = (int)ceil_div(E, SE3_TILE_E);
+  prm.n_ob = Co / SE3_TILE_O;
+  prm.accumulate = accumulate;
+  prm.nk16 = Kp / 16;
+  const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
+  prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 2));
+  prm.band_m = std::max(1, 148 / (csz * prm.band_o));
+  cudaStream_t s = as_stream(stream);
+#define SE3_LR_CASE(PP) (csz == 1 ? launch_lr<PP, 1>(prm, s) : launch_lr<PP, 2>(prm, s))
+  switch (P) {
+    case 1: return SE3_LR_CASE(1);
+    case 3: return SE3_LR_CASE(3);
+    case 5: return SE3_LR_CASE(5);
+    default: return SE3_LR_CASE(7);
+  }
+#undef SE3_LR_CASE
+}

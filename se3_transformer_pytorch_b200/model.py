@@ -192,36 +192,52 @@ class ConvSE3(nn.Module):
         return tuple(v)
 
     def packed(self):
-        """Trunk parameter pack [pairs, stride] + tensor-core images of net.6 (built lazily, rebuilt when weights change)."""
+        """Trunk parameter pack [pairs, stride] (built lazily, rebuilt when weights change) + a cache of the tensor-core
+        images of net.6 for the direct (K = 128) kernel, filled on demand by w3_image()."""
         ver = None if self.free_master else self._param_version()
         if self._packed is not None and (self.free_master or self._packed['version'] == ver):
             return self._packed
         with torch.no_grad():
             trunk = torch.stack([self.kernel_unary[f'({di},{do})'].rp.trunk_params() for di, do in self.pairs]).contiguous()
-            dev = trunk.device
-            images = {}
-            for di, do in self.pairs:
-                pc = self.kernel_unary[f'({di},{do})']
-                if ops.tc_supported(dev, pc.nc_out, pc.d_out):
-                    lin, ln = pc.rp.net['6'], pc.rp.net['4']
-                    # fp16 range guard of the split-precision operands: |g| <= sqrt(127) max|ln.w| + max|ln.b| after
-                    # LayerNorm + GELU; outside it the pair runs on the fp32 SIMT kernel
-                    g_bound = 11.3 * float(ln.weight.abs().max()) + float(ln.bias.abs().max())
-                    if float(lin.weight.abs().max()) < 6.0e4 and g_bound < 6.0e4:
-                        images[(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
-        self._packed = dict(version=ver, trunk=trunk, images=images)
+        self._packed = dict(version=ver, trunk=trunk, images={}, tc_ok={})
         return self._packed
 
-    def pack_weights(self, free_master=False):
-        """Build the packed weights now; with free_master=True the fp32 net.6 weights of tensor-core pairs are
-        released (inference-only: state_dict() no longer holds them)."""
+    def tc_eligible(self, di, do):
+        """The tcgen05 kernels take this pair: sm_100, C_out % 32 == 0, degree_out <= 3 and operands inside the fp16 range
+        of the hi/lo split (|g| <= sqrt(127) max|ln.w| + max|ln.b| after LayerNorm + GELU)."""
         pk = self.packed()
+        if (di, do) not in pk['tc_ok']:
+            pc = self.kernel_unary[f'({di},{do})']
+            ok = ops.tc_supported(pk['trunk'].device, pc.nc_out, pc.d_out)
+            if ok and (di, do) not in pk['images']:
+                lin, ln = pc.rp.net['6'], pc.rp.net['4']
+                g_bound = 11.3 * float(ln.weight.abs().max()) + float(ln.bias.abs().max())
+                ok = g_bound < 6.0e4 and (lin.weight.numel() == 0 or float(lin.weight.abs().max()) < 6.0e4)
+            pk['tc_ok'][(di, do)] = ok
+        return pk['tc_ok'][(di, do)]
+
+    def w3_image(self, di, do):
+        pk = self.packed()
+        if (di, do) not in pk['images']:
+            pc = self.kernel_unary[f'({di},{do})']
+            lin = pc.rp.net['6']
+            with torch.no_grad():
+                pk['images'][(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
+        return pk['images'][(di, do)]
+
+    def pack_weights(self, free_master=False):
+        """Build the direct-kernel weight images now; with free_master=True the fp32 net.6 weights of tensor-core pairs
+        are released (inference-only: state_dict() no longer holds them, and the low-rank path, which needs them, is off)."""
+        for di, do in self.pairs:
+            if self.tc_eligible(di, do):
+                self.w3_image(di, do)
         if free_master:
+            pk = self.packed()
             self.free_master = True
             for key, img in pk['images'].items():
                 lin = self.kernel_unary[f'({key[0]},{key[1]})'].rp.net['6']
                 lin.weight.data = torch.empty(0, device=img.device)
-        return pk
+        return self.packed()
 
     # ---- forward ----------------------------------------------------------------------------------------
     def edge_features(self, edge_info, rel_dist):
@@ -258,10 +274,22 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         pk = conv.packed()
         feat = conv.edge_features(edge_info, rel_dist)
         assert feat.shape[-1] == conv.in_dim, f'edge feature width {feat.shape[-1]} != {conv.in_dim}'
-        use_tc = {p: (p in pk['images']) for p in conv.pairs}
         g = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs))
+        tc_ok = {pair: conv.tc_eligible(*pair) for pair in conv.pairs}
+        # low-rank radial path: G ~= U V^T per pair (verified on this forward's edges), K = r+1 instead of 128
+        lr = {}
+        if ops.lowrank_enabled(E) and not conv.free_master and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
+            fac = ops.lowrank_factor(g)
+            U = torch.zeros((len(conv.pairs), E, 64), dtype=torch.float32, device=dev)
+            for pi, (pair, f) in enumerate(zip(conv.pairs, fac)):
+                if f is None or not tc_ok[pair]:
+                    continue
+                r, V = f
+                U[pi, :, :r] = g[pi] @ V
+                U[pi, :, r] = 1.0
+                lr[pair] = dict(r=r, V=V, Kp=16 * ((r + 1 + 15) // 16), U=U[pi])
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
-        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=use_tc))
+        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr))
 
     # chunk over edge tiles so that the largest T block fits the workspace
     worst = max(ops.t_numel(1, mi, to_order(min(di, do)), to_order(do)) * 4
@@ -282,8 +310,21 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 for st in states:
                     conv = st['conv']
                     out = st['outs'][do][e0:e0 + ec]
-                    if st['use_tc'][(di, do)]:
-                        ops.pairwise_tc(st['g'][pi, e0:e0 + ec], st['pk']['images'][(di, do)], workspace, ec, mo, mi, Fq, P,
+                    if (di, do) in st['lr']:
+                        lrp = st['lr'][(di, do)]
+                        if 'img' not in lrp:                      # F' = [W3 V | b3 | 0] imaged once per forward
+                            lin = conv.kernel_unary[f'({di},{do})'].rp.net['6']
+                            Fp = torch.zeros((lin.weight.shape[0], lrp['Kp']), dtype=torch.float32, device=dev)
+                            Fp[:, :lrp['r']] = lin.weight @ lrp['V']
+                            Fp[:, lrp['r']] = lin.bias
+                            lrp['img'] = ops.pack_lowrank(Fp, mo, mi, Fq, lrp['Kp'])
+                            del Fp
+                        ops.pairwise_lr(lrp['U'][e0:e0 + ec], lrp['img'], workspace, ec, mo, mi, Fq, P, lrp['Kp'], out,
+                                        accumulate=not first)
+                        if t0 + tc >= n_tiles:
+                            del lrp['img']
+                    elif st['use_tc'][(di, do)]:
+                        ops.pairwise_tc(st['g'][pi, e0:e0 + ec], conv.w3_image(di, do), workspace, ec, mo, mi, Fq, P,
                                         out, accumulate=not first)
                     else:
                         lin = conv.kernel_unary[f'({di},{do})'].rp.net['6']

@@ -32,6 +32,9 @@ _SIGNATURES = {
     'se3_pack_w3': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_pairwise_tc_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
     'se3_pairwise_tc_debug': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
+    'se3_lowrank_image_bytes': (c_int64, [c_int, c_int, c_int]),
+    'se3_pack_lowrank': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_pairwise_lr_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
@@ -317,6 +320,60 @@ def pairwise_tc(g, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
         else:
             _check(lib().se3_pairwise_tc_debug(_p(g), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _p(dump),
                                                _stream()))
+
+
+def pack_lowrank(Fp, Co, Ci, F, Kp):
+    """Fp [Co*Ci*F, Kp] fp32 (W3 V | b3 | 0) -> tensor-core operand image for pairwise_lr."""
+    _require_cuda(Fp)
+    nbytes = lib().se3_lowrank_image_bytes(Co, Ci, F)
+    if nbytes < 0:
+        raise RuntimeError(f'pack_lowrank: unsupported shape Co={Co} Ci={Ci} F={F}')
+    img = torch.empty(nbytes, dtype=torch.uint8, device=Fp.device)
+    with torch.cuda.device(Fp.device):
+        _check(lib().se3_pack_lowrank(_p(_f32(Fp)), Co, Ci, F, Kp, _p(img), _stream()))
+    return img
+
+
+def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
+    """Low-rank radial path: U [E,64] fp32 (G V | 1 | 0), w_img from pack_lowrank."""
+    _require_cuda(U, w_img, T, out)
+    # executed work: K = Kp instead of 128 for the GEMM, same contraction with T
+    flops = 2 * E * Co * Ci * F * (Kp + P)
+    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, tag=f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}'):
+        _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
+
+
+def lowrank_factor(G, tol=3e-7, ranks=(15, 31, 47, 63)):
+    """Factor the trunk outputs G [pairs, E, 128] (fp32) of one ConvSE3 as G ~= U V^T per pair.
+    Returns per pair (r, V [128, r] fp32) or None where no rank <= 63 meets  max|G - U V^T| <= tol * max|G|
+    (the residual is measured in float64 on the actual edges of this forward).  One host synchronisation."""
+    Gd = G.double()
+    C = Gd.transpose(1, 2) @ Gd                                   # [pairs, 128, 128]
+    evals, evecs = torch.linalg.eigh(C)                           # ascending
+    gmax = Gd.abs().amax(dim=(1, 2))
+    pairs, E, K = G.shape
+    tails = torch.cumsum(evals.clamp(min=0), dim=1)               # tails[:, j] = sum of the j+1 smallest eigenvalues
+    tails_h, gmax_h = tails.cpu(), gmax.cpu()
+    out = []
+    for p in range(pairs):
+        chosen = None
+        for r in ranks:
+            rms = float((tails_h[p, K - r - 1] / (E * K)).clamp(min=0).sqrt())
+            if rms > tol * float(gmax_h[p]) / 8:                  # cheap screen before the exact check
+                continue
+            V = evecs[p, :, K - r:]
+            res = (Gd[p] - (Gd[p] @ V) @ V.t()).abs().max()
+            if float(res) <= tol * float(gmax_h[p]):
+                chosen = (r, V.float().contiguous())
+                break
+        out.append(chosen)
+    return out
+
+
+def lowrank_enabled(E):
+    if os.environ.get('SE3B200_NO_LOWRANK'):
+        return False
+    return E >= int(os.environ.get('SE3B200_LOWRANK_MIN_EDGES', 16384))
 
 
 def tc_supported(device, Co, P):

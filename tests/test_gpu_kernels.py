@@ -224,6 +224,53 @@ def test_pairwise_tc_cluster_sizes(csz, monkeypatch):
     assert rel_err(out.cpu().numpy(), pr['out']) < 2e-5
 
 
+@pytest.mark.parametrize('r,P,di,do', [(15, 7, 3, 3), (31, 3, 1, 1), (20, 5, 2, 2), (63, 1, 0, 0)])
+def test_pairwise_lowrank_matches_fp64(r, P, di, do):
+    """Low-rank radial kernel: G = U V^T exactly of rank r; result vs float64 of the original (K = 128) contraction."""
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.tc_supported(DEV, 64, P):
+        pytest.skip('tensor-core path needs sm_100')
+    rng = np.random.default_rng(11)
+    Ci, Co = 10, 64
+    pr = _pair_problem(rng, 1, 30, 9, Ci, Co, di, do)             # E = 270 -> 3 edge tiles (one padding CTA in a 2-cluster)
+    E, F = pr['E'], pr['F']
+    Vq, _ = np.linalg.qr(rng.standard_normal((128, r)))
+    Ur = rng.standard_normal((E, r))
+    G = (Ur @ Vq.T)                                                # exactly rank r
+    W3, b3 = pr['W3'].astype(np.float64), pr['b3'].astype(np.float64)
+    R = (G @ W3.T + b3).reshape(E, Co, Ci, F)
+    ref = np.einsum('eoif,eifp->eop', R, pr['T'].reshape(E, Ci, F, P))
+    Kp = 16 * ((r + 1 + 15) // 16)
+    U = np.zeros((E, 64), dtype=np.float32); U[:, :r] = Ur; U[:, r] = 1.0
+    Fp = np.zeros((Co * Ci * F, Kp), dtype=np.float32); Fp[:, :r] = W3 @ Vq; Fp[:, r] = b3
+    T = ops.tbuild(cu(pr['x']), cu(pr['idx']), cu(pr['B']).reshape(-1), di, do)
+    img = ops.pack_lowrank(cu(Fp), Co, Ci, F, Kp)
+    out = torch.full((E, Co, P), 5.0, device=DEV)
+    ops.pairwise_lr(cu(U), img, T, E, Co, Ci, F, P, Kp, out, accumulate=False)
+    assert rel_err(out.cpu().numpy(), ref) < 3e-6
+    ops.pairwise_lr(cu(U), img, T, E, Co, Ci, F, P, Kp, out, accumulate=True)
+    assert rel_err(out.cpu().numpy(), 2 * ref) < 3e-6
+
+
+def test_lowrank_factor_of_radial_trunk():
+    """Distance-only radial trunks are numerically low rank: the factorisation meets its verified tolerance with r <= 31."""
+    from se3_transformer_pytorch_b200 import ops
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(1, 128), torch.nn.LayerNorm(128), torch.nn.GELU(), torch.nn.Linear(128, 128),
+                              torch.nn.LayerNorm(128), torch.nn.GELU()).to(DEV)
+    d = torch.rand(20000, 1, device=DEV) * 3
+    with torch.no_grad():
+        G = net(d)[None]
+    (fac,) = ops.lowrank_factor(G)
+    assert fac is not None and fac[0] <= 31
+    r, V = fac
+    res = (G[0].double() - (G[0].double() @ V.double()) @ V.double().t()).abs().max() / G.abs().max()
+    assert float(res) < 1e-6
+    # unstructured G does not factor: the caller must fall back to the direct kernel
+    (none,) = ops.lowrank_factor(torch.randn(1, 4096, 128, device=DEV))
+    assert none is None
+
+
 def test_pairwise_tc_headline_width_matches_simt():
     """BASELINE cfg2 widths (C_in = C_out = 512, degree 3 -> 3) on a small edge set: tensor-core vs SIMT fp32."""
     from se3_transformer_pytorch_b200 import ops
