@@ -343,10 +343,11 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
         _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
 
 
-def lowrank_factor(G, tol=3e-7, ranks=(15, 31, 47, 63)):
+def lowrank_factor(G, tol=1e-6, ranks=(15, 31, 47, 63)):
     """Factor the trunk outputs G [pairs, E, 128] (fp32) of one ConvSE3 as G ~= U V^T per pair.
     Returns per pair (r, V [128, r] fp32) or None where no rank <= 63 meets  max|G - U V^T| <= tol * max|G|
-    (the residual is measured in float64 on the actual edges of this forward).  One host synchronisation."""
+    (the residual is measured in float64 on the actual edges of this forward).  tol = 1e-6 is a few fp32 ulps of the
+    largest entries: the fp32 LayerNorm/GELU rounding noise of G itself (full rank, ~3e-7) is the floor.  One host sync."""
     Gd = G.double()
     C = Gd.transpose(1, 2) @ Gd                                   # [pairs, 128, 128]
     evals, evecs = torch.linalg.eigh(C)                           # ascending
@@ -359,7 +360,7 @@ def lowrank_factor(G, tol=3e-7, ranks=(15, 31, 47, 63)):
         chosen = None
         for r in ranks:
             rms = float((tails_h[p, K - r - 1] / (E * K)).clamp(min=0).sqrt())
-            if rms > tol * float(gmax_h[p]) / 8:                  # cheap screen before the exact check
+            if rms > tol * float(gmax_h[p]) / 4:                  # cheap screen before the exact check
                 continue
             V = evecs[p, :, K - r:]
             res = (Gd[p] - (Gd[p] @ V) @ V.t()).abs().max()
