@@ -237,8 +237,9 @@ def run_ours(args, wl, rank, local_rank, world):
         model = SE3Transformer(**wl['ctor'])
     model.eval()
     lowrank = ops.lowrank_enabled(wl['b'] * wl['n'] * min(wl['ctor']['num_neighbors'], wl['n'] - 1))
-    if not lowrank:
-        model.pack_weights(free_master=True)     # direct-kernel operand images; fp32 masters of net.6 released (inference)
+    # tensor-core operand images (low-rank plan for distances <= 16 where the radial functions are distance-only, the
+    # direct K=128 image otherwise); fp32 masters of net.6 released (inference)
+    model.pack_weights(free_master=True, max_distance=16.0 if lowrank else None)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     b, n, dim = wl['b'], wl['n'], wl['ctor']['dim']

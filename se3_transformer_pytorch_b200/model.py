@@ -8,6 +8,7 @@ libse3b200.so through `ops`; the cheap glue around it (embeddings, LinearSE3 GEM
 
 Forward only: everything runs under torch.no_grad().  CUDA only: there is no CPU fallback.
 """
+import os
 from math import sqrt
 
 import torch
@@ -136,6 +137,15 @@ class RadialFunc(nn.Module):
             '6': nn.Linear(mid_dim, num_freq * in_dim * out_dim),
         })
 
+    def trunk64(self, feat):
+        """The trunk (net.0 .. net.5) in float64 with torch ops: used off the hot path, to sample the curve g(d) when the
+        low-rank plan of a pair is built."""
+        n = self.net
+        h = F.linear(feat.double(), n['0'].weight.double(), n['0'].bias.double())
+        h = F.gelu(F.layer_norm(h, (h.shape[-1],), n['1'].weight.double(), n['1'].bias.double()))
+        h = F.linear(h, n['3'].weight.double(), n['3'].bias.double())
+        return F.gelu(F.layer_norm(h, (h.shape[-1],), n['4'].weight.double(), n['4'].bias.double()))
+
     def trunk_params(self):
         n = self.net
         return torch.cat([n['0'].weight.t().reshape(-1), n['0'].bias, n['1'].weight, n['1'].bias,
@@ -225,18 +235,72 @@ class ConvSE3(nn.Module):
                 pk['images'][(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
         return pk['images'][(di, do)]
 
-    def pack_weights(self, free_master=False):
-        """Build the direct-kernel weight images now; with free_master=True the fp32 net.6 weights of tensor-core pairs
-        are released (inference-only: state_dict() no longer holds them, and the low-rank path, which needs them, is off)."""
+    # ---- low-rank radial path ----------------------------------------------------------------------------
+    LR_GRID = 16384          # float64 samples of g(d) per pair when a plan is built
+    LR_RUNTIME_TOL = 1e-5    # sanity bound on max|G - (G V) V^T| / max|G| of the fp32 trunk outputs of a forward
+
+    def encode_dist(self, rd):
+        """[..., 1] distances -> radial-MLP input (reference utils.py:96-104 when fourier_encode_dist)."""
+        if not self.fourier_encode_dist:
+            return rd
+        scales = 2 ** torch.arange(self.num_fourier_features, device=rd.device, dtype=rd.dtype)
+        xs = rd / scales
+        return torch.cat([xs.sin(), xs.cos(), rd], dim=-1)
+
+    def lowrank_plan(self, d_max):
+        """Per pair: orthonormal V [128, r] spanning the curve g(d), d in [0, D], and the tensor-core image of
+        F'' = [W3 V | b3 | 0].  Depends on the weights and on D only: built once (and again if weights change or a forward
+        brings a larger distance).  Only for distance-only radial functions (no extra edge features)."""
+        pk = self.packed()
+        plan = pk.get('lr')
+        if plan is not None and plan['D'] >= d_max:
+            return plan
+        dev = pk['trunk'].device
+        D = 1.25 * d_max
+        with torch.no_grad():
+            grid = torch.linspace(0.0, D, self.LR_GRID, device=dev, dtype=torch.float64).unsqueeze(-1)
+            feat = self.encode_dist(grid)
+            pairs = {}
+            for di, do in self.pairs:
+                if not self.tc_eligible(di, do):
+                    continue
+                pc = self.kernel_unary[f'({di},{do})']
+                lin = pc.rp.net['6']
+                if lin.weight.numel() == 0:
+                    continue
+                basis = ops.lowrank_basis(pc.rp.trunk64(feat))
+                if basis is None:
+                    continue
+                r, V = basis
+                Kp = 16 * ((r + 1 + 15) // 16)
+                Fp = torch.zeros((lin.weight.shape[0], Kp), dtype=torch.float32, device=dev)
+                Fp[:, :r] = (lin.weight.double() @ V).float()
+                Fp[:, r] = lin.bias
+                Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
+                Vp[:, :r] = V.float()
+                pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=ops.pack_lowrank(Fp, pc.nc_out, pc.nc_in, pc.num_freq, Kp))
+                del Fp
+        plan = dict(D=D, pairs=pairs)
+        pk['lr'] = plan
+        return plan
+
+    def pack_weights(self, free_master=False, max_distance=None):
+        """Build the tensor-core weight images now.  With max_distance (an upper bound on the neighbour distances the model
+        will see) and distance-only radial functions, the low-rank plan is built and pairs it covers need no direct
+        (K = 128) image.  free_master=True then releases the fp32 net.6 weights of every imaged pair (inference only:
+        state_dict() no longer holds them)."""
+        covered = {}
+        if max_distance is not None and self.edge_dim == 0 and not os.environ.get('SE3B200_NO_LOWRANK'):
+            covered = self.lowrank_plan(float(max_distance) / 1.25)['pairs']
         for di, do in self.pairs:
-            if self.tc_eligible(di, do):
+            if self.tc_eligible(di, do) and (di, do) not in covered:
                 self.w3_image(di, do)
         if free_master:
             pk = self.packed()
             self.free_master = True
-            for key, img in pk['images'].items():
+            for key in list(pk['images']) + list(covered):
                 lin = self.kernel_unary[f'({key[0]},{key[1]})'].rp.net['6']
-                lin.weight.data = torch.empty(0, device=img.device)
+                lin.weight.data = torch.empty(0, device=pk['trunk'].device)
         return self.packed()
 
     # ---- forward ----------------------------------------------------------------------------------------
@@ -276,18 +340,31 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         assert feat.shape[-1] == conv.in_dim, f'edge feature width {feat.shape[-1]} != {conv.in_dim}'
         g = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs))
         tc_ok = {pair: conv.tc_eligible(*pair) for pair in conv.pairs}
-        # low-rank radial path: G ~= U V^T per pair (verified on this forward's edges), K = r+1 instead of 128
-        lr = {}
-        if ops.lowrank_enabled(E) and not conv.free_master and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
-            fac = ops.lowrank_factor(g)
+        # low-rank radial path (distance-only radial functions): U = G V with the pair's cached basis, K = r+1 <= 64
+        lr, plan = {}, None
+        if conv.edge_dim == 0 and ops.lowrank_enabled(E) and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
+            if conv.free_master:
+                plan = pk.get('lr')                 # built by pack_weights(max_distance=...) before the masters went away
+            else:
+                plan = conv.lowrank_plan(float(rel_dist.max()))      # cached; one host sync for the distance range
+        if plan is not None and plan['pairs']:
             U = torch.zeros((len(conv.pairs), E, 64), dtype=torch.float32, device=dev)
-            for pi, (pair, f) in enumerate(zip(conv.pairs, fac)):
-                if f is None or not tc_ok[pair]:
+            worst = torch.zeros((), dtype=torch.float32, device=dev)
+            for pi, pair in enumerate(conv.pairs):
+                pp = plan['pairs'].get(pair)
+                if pp is None:
                     continue
-                r, V = f
-                U[pi, :, :r] = g[pi] @ V
-                U[pi, :, r] = 1.0
-                lr[pair] = dict(r=r, V=V, Kp=16 * ((r + 1 + 15) // 16), U=U[pi])
+                torch.matmul(g[pi], pp['V'], out=U[pi])
+                res = (g[pi] - U[pi] @ pp['V'].t()).abs().max() / g[pi].abs().max().clamp(min=1e-30)
+                worst = torch.maximum(worst, res)
+                U[pi, :, pp['r']] = 1.0
+                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'])
+            if float(worst) > conv.LR_RUNTIME_TOL:
+                # the fp32 trunk outputs of this forward leave the cached subspace (distances beyond the plan's range)
+                if conv.free_master:
+                    raise RuntimeError(f'low-rank radial plan does not cover this input (residual {float(worst):.1e}); '
+                                       'pack_weights(max_distance=...) was given too small a distance')
+                lr = {}                              # evaluate this ConvSE3 with the direct K = 128 kernel
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
         states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr))
 
@@ -312,17 +389,8 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                     out = st['outs'][do][e0:e0 + ec]
                     if (di, do) in st['lr']:
                         lrp = st['lr'][(di, do)]
-                        if 'img' not in lrp:                      # F' = [W3 V | b3 | 0] imaged once per forward
-                            lin = conv.kernel_unary[f'({di},{do})'].rp.net['6']
-                            Fp = torch.zeros((lin.weight.shape[0], lrp['Kp']), dtype=torch.float32, device=dev)
-                            Fp[:, :lrp['r']] = lin.weight @ lrp['V']
-                            Fp[:, lrp['r']] = lin.bias
-                            lrp['img'] = ops.pack_lowrank(Fp, mo, mi, Fq, lrp['Kp'])
-                            del Fp
                         ops.pairwise_lr(lrp['U'][e0:e0 + ec], lrp['img'], workspace, ec, mo, mi, Fq, P, lrp['Kp'], out,
                                         accumulate=not first)
-                        if t0 + tc >= n_tiles:
-                            del lrp['img']
                     elif st['use_tc'][(di, do)]:
                         ops.pairwise_tc(st['g'][pi, e0:e0 + ec], conv.w3_image(di, do), workspace, ec, mo, mi, Fq, P,
                                         out, accumulate=not first)
@@ -582,10 +650,11 @@ class SE3Transformer(nn.Module):
     def conv_modules(self):
         return [m for m in self.modules() if isinstance(m, ConvSE3)]
 
-    def pack_weights(self, free_master=False):
-        """Pre-build the tensor-core weight images of every ConvSE3 (otherwise done lazily on the first forward)."""
+    def pack_weights(self, free_master=False, max_distance=None):
+        """Pre-build the tensor-core weight images of every ConvSE3 (otherwise done lazily on the first forward); see
+        ConvSE3.pack_weights."""
         for m in self.conv_modules():
-            m.pack_weights(free_master=free_master)
+            m.pack_weights(free_master=free_master, max_distance=max_distance)
         return self
 
     def graphed(self, feats, coors, mask=None, **fwd_kwargs):

@@ -343,32 +343,19 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
         _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
 
 
-def lowrank_factor(G, tol=1e-6, ranks=(15, 31, 47, 63)):
-    """Factor the trunk outputs G [pairs, E, 128] (fp32) of one ConvSE3 as G ~= U V^T per pair.
-    Returns per pair (r, V [128, r] fp32) or None where no rank <= 63 meets  max|G - U V^T| <= tol * max|G|
-    (the residual is measured in float64 on the actual edges of this forward).  tol = 1e-6 is a few fp32 ulps of the
-    largest entries: the fp32 LayerNorm/GELU rounding noise of G itself (full rank, ~3e-7) is the floor.  One host sync."""
-    Gd = G.double()
-    C = Gd.transpose(1, 2) @ Gd                                   # [pairs, 128, 128]
-    evals, evecs = torch.linalg.eigh(C)                           # ascending
-    gmax = Gd.abs().amax(dim=(1, 2))
-    pairs, E, K = G.shape
-    tails = torch.cumsum(evals.clamp(min=0), dim=1)               # tails[:, j] = sum of the j+1 smallest eigenvalues
-    tails_h, gmax_h = tails.cpu(), gmax.cpu()
-    out = []
-    for p in range(pairs):
-        chosen = None
-        for r in ranks:
-            rms = float((tails_h[p, K - r - 1] / (E * K)).clamp(min=0).sqrt())
-            if rms > tol * float(gmax_h[p]) / 4:                  # cheap screen before the exact check
-                continue
-            V = evecs[p, :, K - r:]
-            res = (Gd[p] - (Gd[p] @ V) @ V.t()).abs().max()
-            if float(res) <= tol * float(gmax_h[p]):
-                chosen = (r, V.float().contiguous())
-                break
-        out.append(chosen)
-    return out
+def lowrank_basis(G64, tol=2e-7, ranks=(15, 31, 47, 63)):
+    """Orthonormal basis of the row space of G64 [S, 128] (float64 samples of a radial trunk along its input curve):
+    returns (r, V [128, r] float64) for the smallest listed rank with  max|G - (G V) V^T| <= tol * max|G|, else None.
+    QR + SVD of the triangular factor (no Gram matrix, so the small singular directions stay accurate)."""
+    _, Rm = torch.linalg.qr(G64)
+    _, _, Vh = torch.linalg.svd(Rm)
+    gmax = float(G64.abs().max())
+    for r in ranks:
+        V = Vh[:r].t().contiguous()
+        res = float((G64 - (G64 @ V) @ V.t()).abs().max())
+        if res <= tol * gmax:
+            return r, V
+    return None
 
 
 def lowrank_enabled(E):
