@@ -26,8 +26,14 @@ namespace se3 {
 
 constexpr int kLrThreads = 640;
 constexpr uint32_t kLrUnitBytes = 2 * kSubBytes;   // one W tile: [hi 16 KiB | lo 16 KiB], K padded to 64
-constexpr int kLrWSlots = 4;
-constexpr int kLrTStages = 4;
+#ifndef SE3_LR_W_SLOTS
+#define SE3_LR_W_SLOTS 4
+#endif
+#ifndef SE3_LR_T_STAGES
+#define SE3_LR_T_STAGES 4
+#endif
+constexpr int kLrWSlots = SE3_LR_W_SLOTS;
+constexpr int kLrTStages = SE3_LR_T_STAGES;
 constexpr uint32_t kLrTmemCols = 512;              // 2 accumulator buffers (256) + A hi (32) + A lo (32)
 constexpr uint32_t kLrAHi = 256, kLrALo = 288;
 constexpr uint32_t kLrIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // fp16 x fp16 -> fp32, M128 N128
@@ -62,7 +68,7 @@ struct LrParams {
   const float* T;
   float* out;
   int64_t E;
-  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, dbg;
 };
 
 template <int P, int CSZ>
@@ -74,6 +80,7 @@ pairwise_lr_kernel(const LrParams prm) {
   float* __restrict__ out = prm.out;
   const int64_t E = prm.E;
   const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, nk16 = prm.nk16;
+  const int dbg = prm.dbg;                                     // timing experiments only (0 in production)
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;
   extern __shared__ uint8_t smem_raw[];
@@ -197,7 +204,7 @@ pairwise_lr_kernel(const LrParams prm) {
             const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
             for (int k16 = 0; k16 < nk16; ++k16) {
               const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
-              tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
+              if (!(dbg & 2)) tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
               accum = 1;
             }
           }
@@ -258,8 +265,15 @@ pairwise_lr_kernel(const LrParams prm) {
       tc_fence_after();
       const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + oq * 8);
       uint32_t r[4][8];
+      if (!(dbg & 4)) {
 #pragma unroll
-      for (int ifl = 0; ifl < 4; ++ifl) tmem_ld8(tcol + (uint32_t)(ifl * 32), r[ifl]);
+        for (int ifl = 0; ifl < 4; ++ifl) tmem_ld8(tcol + (uint32_t)(ifl * 32), r[ifl]);
+      } else {
+#pragma unroll
+        for (int ifl = 0; ifl < 4; ++ifl)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[ifl][j] = (uint32_t)(s + j);
+      }
       mbar_wait(bar_t_full + 8 * ts, tph);
       const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + ts * kTBytes);
       tmem_ld_wait();
@@ -274,6 +288,12 @@ pairwise_lr_kernel(const LrParams prm) {
         for (int h4 = 0; h4 < PH; ++h4) {
           const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
           tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
+        }
+        if (dbg & 1) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            acc[a][0] = add2(acc[a][0], pack2(__uint_as_float(r[ifl][2 * a]) + tv[0], __uint_as_float(r[ifl][2 * a + 1])));
+          continue;
         }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
@@ -390,6 +410,7 @@ extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const floa
   prm.n_ob = Co / SE3_TILE_O;
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
+  prm.dbg = lr_env_int("SE3B200_LR_DEBUG", 0);
   const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
   prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 2));
   prm.band_m = std::max(1, 148 / (csz * prm.band_o));
