@@ -68,7 +68,7 @@ struct LrParams {
   const float* T;
   float* out;
   int64_t E;
-  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, dbg;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o;
 };
 
 template <int P, int CSZ>
@@ -80,7 +80,6 @@ pairwise_lr_kernel(const LrParams prm) {
   float* __restrict__ out = prm.out;
   const int64_t E = prm.E;
   const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, nk16 = prm.nk16;
-  const int dbg = prm.dbg;                                     // timing experiments only (0 in production)
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;
   extern __shared__ uint8_t smem_raw[];
@@ -204,7 +203,7 @@ pairwise_lr_kernel(const LrParams prm) {
             const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
             for (int k16 = 0; k16 < nk16; ++k16) {
               const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
-              if (!(dbg & 2)) tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
+              tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
               accum = 1;
             }
           }
@@ -256,55 +255,70 @@ pairwise_lr_kernel(const LrParams prm) {
 #pragma unroll
       for (int p = 0; p < P; ++p) acc[a][p] = 0ull;
 
+    // The step loop is software pipelined at the granularity of one (i,f) slot (8 accumulator columns, PH T quads):
+    // while slot c is contracted, the tcgen05.ld and the LDS of slot c+1 are in flight (tcgen05.wait::ld waits for every
+    // outstanding load, so it is placed after the FMAs of the current slot).
+    const uint32_t tcol0 = tmem_base + t_lane + (uint32_t)(oq * 8);
+    const float4* Tsm = reinterpret_cast<const float4*>(base_ptr + (sT - base)) + el;
+    auto contract = [&](const uint32_t (&r)[8], const float4 (&t)[PH]) {
+      float tv[PH * 4];
+#pragma unroll
+      for (int h4 = 0; h4 < PH; ++h4) { tv[h4 * 4 + 0] = t[h4].x; tv[h4 * 4 + 1] = t[h4].y; tv[h4 * 4 + 2] = t[h4].z; tv[h4 * 4 + 3] = t[h4].w; }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const unsigned long long t2 = pack2(tv[p], tv[p]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          acc[a][p] = fma2(pack2(__uint_as_float(r[2 * a]), __uint_as_float(r[2 * a + 1])), t2, acc[a][p]);
+      }
+    };
+    auto load_t = [&](float4 (&t)[PH], int stage, int ifl) {
+#pragma unroll
+      for (int h4 = 0; h4 < PH; ++h4) t[h4] = Tsm[(size_t)stage * (kTBytes / 16) + (ifl * PH + h4) * 128];
+    };
+    uint32_t ra[8], rb[8];
+    float4 ta[PH], tb[PH];
+    mbar_wait(bar_tm_full, 0);
+    tc_fence_after();
+    tmem_ld8(tcol0, ra);
+    mbar_wait(bar_t_full, 0);
+    load_t(ta, 0, 0);
+    tmem_ld_wait();
     for (int s = 0; s < NIFB; ++s) {
       const int st = s & 1;
-      const uint32_t ph = (uint32_t)(s >> 1) & 1u;
       const int ts = s % kLrTStages;
-      const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
-      mbar_wait(bar_tm_full + 8 * st, ph);
-      tc_fence_after();
-      const uint32_t tcol = tmem_base + t_lane + (uint32_t)(st * 128 + oq * 8);
-      uint32_t r[4][8];
-      if (!(dbg & 4)) {
-#pragma unroll
-        for (int ifl = 0; ifl < 4; ++ifl) tmem_ld8(tcol + (uint32_t)(ifl * 32), r[ifl]);
-      } else {
-#pragma unroll
-        for (int ifl = 0; ifl < 4; ++ifl)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r[ifl][j] = (uint32_t)(s + j);
-      }
-      mbar_wait(bar_t_full + 8 * ts, tph);
-      const float4* Ts = reinterpret_cast<const float4*>(base_ptr + (sT - base) + ts * kTBytes);
+      const uint32_t tcol = tcol0 + (uint32_t)(st * 128);
+      // slot 0
+      tmem_ld8(tcol + 32u, rb);
+      load_t(tb, ts, 1);
+      contract(ra, ta);
       tmem_ld_wait();
-      // all accumulator reads of this step have landed in registers: give the buffer back to the MMA warp
+      // slot 1
+      tmem_ld8(tcol + 64u, ra);
+      load_t(ta, ts, 2);
+      contract(rb, tb);
+      tmem_ld_wait();
+      // slot 2
+      tmem_ld8(tcol + 96u, rb);
+      load_t(tb, ts, 3);
+      contract(ra, ta);
+      tmem_ld_wait();
+      // every accumulator column of this step is in registers: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
-#pragma unroll
-      for (int ifl = 0; ifl < 4; ++ifl) {
-        float tv[PH * 4];
-#pragma unroll
-        for (int h4 = 0; h4 < PH; ++h4) {
-          const float4 t4 = Ts[(ifl * PH + h4) * 128 + el];
-          tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
-        }
-        if (dbg & 1) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            acc[a][0] = add2(acc[a][0], pack2(__uint_as_float(r[ifl][2 * a]) + tv[0], __uint_as_float(r[ifl][2 * a + 1])));
-          continue;
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const unsigned long long t2 = pack2(tv[p], tv[p]);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const unsigned long long R2 = pack2(__uint_as_float(r[ifl][2 * a]), __uint_as_float(r[ifl][2 * a + 1]));
-            acc[a][p] = fma2(R2, t2, acc[a][p]);
-          }
-        }
+      // slot 3, with slot 0 of the next step in flight
+      const bool more = s + 1 < NIFB;
+      if (more) {
+        const int s1 = s + 1;
+        mbar_wait(bar_tm_full + 8 * (s1 & 1), (uint32_t)(s1 >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld8(tcol0 + (uint32_t)((s1 & 1) * 128), ra);
+        mbar_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
+        load_t(ta, s1 % kLrTStages, 0);
       }
+      contract(rb, tb);
+      if (more) tmem_ld_wait();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
     }
@@ -410,7 +424,6 @@ extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const floa
   prm.n_ob = Co / SE3_TILE_O;
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
-  prm.dbg = lr_env_int("SE3B200_LR_DEBUG", 0);
   const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
   prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 2));
   prm.band_m = std::max(1, 148 / (csz * prm.band_o));
