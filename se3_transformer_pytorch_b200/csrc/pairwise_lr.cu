@@ -34,8 +34,9 @@ constexpr uint32_t kLrUnitBytes = 2 * kSubBytes;   // one W tile: [hi 16 KiB | l
 #endif
 constexpr int kLrWSlots = SE3_LR_W_SLOTS;
 constexpr int kLrTStages = SE3_LR_T_STAGES;
-constexpr uint32_t kLrTmemCols = 512;              // 2 accumulator buffers (256) + A hi (32) + A lo (32)
-constexpr uint32_t kLrAHi = 256, kLrALo = 288;
+constexpr int kLrAcc = 3;                          // TMEM accumulator buffers (the MMA -> epilogue -> MMA round trip is long)
+constexpr uint32_t kLrTmemCols = 512;              // 3 accumulator buffers (384) + A hi (32) + A lo (32)
+constexpr uint32_t kLrAHi = 384, kLrALo = 416;
 constexpr uint32_t kLrIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // fp16 x fp16 -> fp32, M128 N128
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -68,10 +69,17 @@ struct LrParams {
   const float* T;
   float* out;
   int64_t E;
-  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, stagger;
+  unsigned long long* trace;   // diagnostic: per-role clock64 stamps of CTA 0 ([5 roles][64 steps][8 events]) or nullptr
 };
 
-template <int P, int CSZ>
+__device__ __forceinline__ void lr_stamp(unsigned long long* trace, int role, int step, int ev) {
+  if (trace != nullptr && blockIdx.x == 0 && step < 64 && (threadIdx.x & 31) == 0) trace[(role * 64 + step) * 8 + ev] = clock64();
+}
+
+// MODE selects the epilogue pipelining: 0 = one (i,f) slot ahead (best for P >= 5), 1 = two-slot batches, 2 = whole steps
+// (best for P <= 3).
+template <int P, int CSZ, int MODE>
 __global__ void __launch_bounds__(kLrThreads, 1)
 pairwise_lr_kernel(const LrParams prm) {
   const float* __restrict__ U = prm.U;
@@ -94,12 +102,12 @@ pairwise_lr_kernel(const LrParams prm) {
   const uint32_t bar_w_empty = bar_w_full + 8 * kLrWSlots;
   const uint32_t bar_t_full = bar_w_empty + 8 * kLrWSlots;
   const uint32_t bar_t_empty = bar_t_full + 8 * kLrTStages;
-  const uint32_t bar_tm_full = bar_t_empty + 8 * kLrTStages;  // [2]
-  const uint32_t bar_tm_empty = bar_tm_full + 16;             // [2]
-  const uint32_t s_tmem_slot = bar_tm_empty + 16;
+  const uint32_t bar_tm_full = bar_t_empty + 8 * kLrTStages;  // [kLrAcc]
+  const uint32_t bar_tm_empty = bar_tm_full + 8 * kLrAcc;     // [kLrAcc]
+  const uint32_t s_tmem_slot = bar_tm_empty + 8 * kLrAcc;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const uint32_t crank = (CSZ > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
   int64_t mt;
@@ -131,7 +139,7 @@ pairwise_lr_kernel(const LrParams prm) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 16);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kLrAcc; ++s) {
       mbar_init(bar_tm_full + 8 * s, 1);
       mbar_init(bar_tm_empty + 8 * s, 16);
     }
@@ -151,14 +159,16 @@ pairwise_lr_kernel(const LrParams prm) {
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
-      // ===================== W producer =====================
-      if (lane == 0) {
-        const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kLrUnitBytes;
-        constexpr uint32_t kShare = kLrUnitBytes / CSZ;
-        for (int s = 0; s < NIFB; ++s) {
-          const int slot = s % kLrWSlots;
-          const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
-          mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
+      // ===================== W producer (warp-uniform loop, one elected lane issues) =====================
+      const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kLrUnitBytes;
+      constexpr uint32_t kShare = kLrUnitBytes / CSZ;
+      for (int s = 0; s < NIFB; ++s) {
+        const int slot = s % kLrWSlots;
+        const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
+        lr_stamp(prm.trace, 3, s, 0);
+        mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
+        lr_stamp(prm.trace, 3, s, 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kLrUnitBytes);
           if (CSZ == 1) {
             bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)s * kLrUnitBytes, kLrUnitBytes, bar_w_full + 8 * slot);
@@ -167,34 +177,41 @@ pairwise_lr_kernel(const LrParams prm) {
                         bar_w_full + 8 * slot, kMask);
           }
         }
+        __syncwarp();
       }
     } else if (warp == 2) {
       // ===================== T producer =====================
-      if (lane == 0) {
-        const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
-        for (int s = 0; s < NIFB; ++s) {
-          const int ts = s % kLrTStages;
-          const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
-          mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
+      const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(T) + (size_t)mt * NIFB * kTBytes;
+      for (int s = 0; s < NIFB; ++s) {
+        const int ts = s % kLrTStages;
+        const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
+        lr_stamp(prm.trace, 4, s, 0);
+        mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
+        lr_stamp(prm.trace, 4, s, 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes);
           bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * ts);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        mbar_wait(bar_a_full, 0);
+      // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      for (int s = 0; s < NIFB; ++s) {
+        const int st = s % kLrAcc;
+        const uint32_t ph = (uint32_t)(s / kLrAcc) & 1u;
+        const int slot = s % kLrWSlots;
+        const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
+        lr_stamp(prm.trace, 0, s, 0);
+        mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
+        lr_stamp(prm.trace, 0, s, 1);
+        mbar_wait(bar_w_full + 8 * slot, wph);
+        lr_stamp(prm.trace, 0, s, 2);
         tc_fence_after();
-        for (int s = 0; s < NIFB; ++s) {
-          const int st = s & 1;
-          const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-          const int slot = s % kLrWSlots;
-          const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
-          mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
-          mbar_wait(bar_w_full + 8 * slot, wph);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
-          const uint32_t wbase = sW + slot * kLrUnitBytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
+        const uint32_t wbase = sW + slot * kLrUnitBytes;
+        if (elect_one()) {
           uint32_t accum = 0;
           // pass 0: U_hi x F_hi   pass 1: U_lo x F_hi   pass 2: U_hi x F_lo
 #pragma unroll
@@ -211,6 +228,8 @@ pairwise_lr_kernel(const LrParams prm) {
           else tc_commit_mc(bar_w_empty + 8 * slot, kMask);
           tc_commit(bar_tm_full + 8 * st);
         }
+        __syncwarp();
+        lr_stamp(prm.trace, 0, s, 4);
       }
     }
   } else {
@@ -255,6 +274,7 @@ pairwise_lr_kernel(const LrParams prm) {
 #pragma unroll
       for (int p = 0; p < P; ++p) acc[a][p] = 0ull;
 
+    if constexpr (MODE == 0) {
     // The step loop is software pipelined at the granularity of one (i,f) slot (8 accumulator columns, PH T quads):
     // while slot c is contracted, the tcgen05.ld and the LDS of slot c+1 are in flight (tcgen05.wait::ld waits for every
     // outstanding load, so it is placed after the FMAs of the current slot).
@@ -285,7 +305,7 @@ pairwise_lr_kernel(const LrParams prm) {
     load_t(ta, 0, 0);
     tmem_ld_wait();
     for (int s = 0; s < NIFB; ++s) {
-      const int st = s & 1;
+      const int st = s % kLrAcc;
       const int ts = s % kLrTStages;
       const uint32_t tcol = tcol0 + (uint32_t)(st * 128);
       // slot 0
@@ -311,9 +331,9 @@ pairwise_lr_kernel(const LrParams prm) {
       const bool more = s + 1 < NIFB;
       if (more) {
         const int s1 = s + 1;
-        mbar_wait(bar_tm_full + 8 * (s1 & 1), (uint32_t)(s1 >> 1) & 1u);
+        mbar_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
         tc_fence_after();
-        tmem_ld8(tcol0 + (uint32_t)((s1 & 1) * 128), ra);
+        tmem_ld8(tcol0 + (uint32_t)((s1 % kLrAcc) * 128), ra);
         mbar_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
         load_t(ta, s1 % kLrTStages, 0);
       }
@@ -321,6 +341,116 @@ pairwise_lr_kernel(const LrParams prm) {
       if (more) tmem_ld_wait();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
+    }
+    } else {
+    // The step loop is software pipelined in batches of G (i,f) slots (8 accumulator columns each): while the current
+    // batch is contracted, the tcgen05.ld of the next batch is in flight.  tcgen05.wait::ld waits for every outstanding
+    // load, so it sits after the FMAs of the current batch; G is chosen so that those FMAs cover the TMEM latency:
+    // G = 2 for P >= 5 (register budget 104: 56 accumulators + 2 x 16 staging), G = 4 (a whole step) for P <= 3.
+    constexpr int G = (MODE == 1) ? 2 : 4;
+    const uint32_t tcol0 = tmem_base + t_lane + (uint32_t)(oq * 8);
+    const float4* Tsm = reinterpret_cast<const float4*>(base_ptr + (sT - base)) + el;
+    auto contract = [&](const uint32_t* r, int stage, int ifl) {          // one slot: 8 columns x P
+      float tv[PH * 4];
+#pragma unroll
+      for (int h4 = 0; h4 < PH; ++h4) {
+        const float4 t4 = Tsm[(size_t)stage * (kTBytes / 16) + (ifl * PH + h4) * 128];
+        tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const unsigned long long t2 = pack2(tv[p], tv[p]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          acc[a][p] = fma2(pack2(__uint_as_float(r[2 * a]), __uint_as_float(r[2 * a + 1])), t2, acc[a][p]);
+      }
+    };
+    auto issue = [&](uint32_t (&r)[G][8], int step, int first_slot) {     // G tcgen05.ld of 8 columns each
+      const uint32_t tcol = tcol0 + (uint32_t)((step % kLrAcc) * 128 + first_slot * 32);
+#pragma unroll
+      for (int j = 0; j < G; ++j) tmem_ld8(tcol + (uint32_t)(j * 32), r[j]);
+    };
+    auto wait_acc = [&](int step) {
+      mbar_wait(bar_tm_full + 8 * (step % kLrAcc), (uint32_t)(step / kLrAcc) & 1u);
+      tc_fence_after();
+    };
+    auto wait_t = [&](int step) { mbar_wait(bar_t_full + 8 * (step % kLrTStages), (uint32_t)(step / kLrTStages) & 1u); };
+    auto release_acc = [&](int step) {                                      // all loads of `step` have completed
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tm_empty + 8 * (step % kLrAcc));
+    };
+    auto release_t = [&](int step) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * (step % kLrTStages));
+    };
+    // De-phase the four epilogue warps of each SM sub-partition (same q, oq = 0..3) by a quarter of a step: every warp
+    // alternates an FMA phase with a synchronisation phase (tcgen05.ld latency, mbarrier round trips); left in lockstep
+    // they all sit in the synchronisation phase together and the FMA pipe idles half of the time (measured).
+    if (prm.stagger > 0 && oq > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)oq * prm.stagger) {
+      }
+    }
+    uint32_t ra[G][8], rb[G][8];
+    wait_acc(0);
+    issue(ra, 0, 0);
+    tmem_ld_wait();
+    if constexpr (G == 2) {
+      wait_t(0);
+      for (int s = 0; s < NIFB; ++s) {
+        const int ts = s % kLrTStages;
+        const bool more = s + 1 < NIFB;
+        const int s1 = s + 1;
+        issue(rb, s, 2);                        // slots 2,3 of this step
+        // probe the next step's barriers now and consume the answers after the FMAs: an mbarrier try_wait costs ~100
+        // cycles of latency even when the phase has long completed
+        uint32_t acc_ok = 1, t_ok = 1;
+        if (more) {
+          acc_ok = mbar_try_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
+          t_ok = mbar_try_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
+        }
+        contract(ra[0], ts, 0);
+        contract(ra[1], ts, 1);
+        tmem_ld_wait();
+        release_acc(s);
+        if (more) {
+          if (!acc_ok) mbar_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
+          tc_fence_after();
+          issue(ra, s1, 0);
+        }
+        contract(rb[0], ts, 2);
+        contract(rb[1], ts, 3);
+        if (more) tmem_ld_wait();
+        release_t(s);
+        if (more && !t_ok) wait_t(s1);
+      }
+    } else {
+      // whole-step batches: ra holds the current step, rb receives the next one (roles swap every step)
+      if (NIFB == 1) release_acc(0);
+      for (int s = 0; s < NIFB; s += 2) {
+        {
+          const bool more = s + 1 < NIFB;
+          if (more) { wait_acc(s + 1); issue(rb, s + 1, 0); }
+          if (s == 0 && more) release_acc(0);   // step 0 was loaded in the prologue
+          wait_t(s);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) contract(ra[j], s % kLrTStages, j);
+          if (more) { tmem_ld_wait(); release_acc(s + 1); }
+          release_t(s);
+        }
+        if (s + 1 < NIFB) {
+          const int s1 = s + 1;
+          const bool more = s1 + 1 < NIFB;
+          if (more) { wait_acc(s1 + 1); issue(ra, s1 + 1, 0); }
+          wait_t(s1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) contract(rb[j], s1 % kLrTStages, j);
+          if (more) { tmem_ld_wait(); release_acc(s1 + 1); }
+          release_t(s1);
+        }
+      }
+    }
     }
     // write out[e, ob*32 + oq*8 + (0..7), 0..P)
     const int64_t e = mt * SE3_TILE_E + el;
@@ -356,10 +486,10 @@ static size_t lr_smem_bytes() {
   return 1024 + kLrWSlots * kLrUnitBytes + kLrTStages * (PH * 8192u) + 256;
 }
 
-template <int P, int CSZ>
+template <int P, int CSZ, int MODE>
 static int launch_lr(const LrParams& prm, cudaStream_t s) {
   const size_t smem = lr_smem_bytes<P>();
-  auto kern = pairwise_lr_kernel<P, CSZ>;
+  auto kern = pairwise_lr_kernel<P, CSZ, MODE>;
   SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_mg = (prm.n_mt + CSZ - 1) / CSZ;
   cudaLaunchConfig_t cfg = {};
@@ -404,8 +534,8 @@ extern "C" int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, 
   return SE3_OK;
 }
 
-extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
-                                   int Kp, int accumulate, float* out, void* stream) {
+static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P, int Kp,
+                            int accumulate, float* out, unsigned long long* trace, void* stream) {
   using namespace se3;
   SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_lr_fwd: bad sizes");
   SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_lr_fwd: Co=%d must be a multiple of %d", Co, SE3_TILE_O);
@@ -424,11 +554,15 @@ extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const floa
   prm.n_ob = Co / SE3_TILE_O;
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
+  prm.trace = trace;
+  prm.stagger = lr_env_int("SE3B200_LR_STAGGER", 0);
   const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
   prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 2));
   prm.band_m = std::max(1, 148 / (csz * prm.band_o));
   cudaStream_t s = as_stream(stream);
-#define SE3_LR_CASE(PP) (csz == 1 ? launch_lr<PP, 1>(prm, s) : launch_lr<PP, 2>(prm, s))
+  const int mode_hi = lr_env_int("SE3B200_LR_MODE_HI", 0), mode_lo = lr_env_int("SE3B200_LR_MODE_LO", 0);
+#define SE3_LR_MODE(PP, M) (csz == 1 ? launch_lr<PP, 1, M>(prm, s) : launch_lr<PP, 2, M>(prm, s))
+#define SE3_LR_CASE(PP) ((PP >= 5 ? mode_hi : mode_lo) == 0 ? SE3_LR_MODE(PP, 0) : (PP >= 5 ? mode_hi : mode_lo) == 1 ? SE3_LR_MODE(PP, 1) : SE3_LR_MODE(PP, 2))
   switch (P) {
     case 1: return SE3_LR_CASE(1);
     case 3: return SE3_LR_CASE(3);
@@ -436,4 +570,16 @@ extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const floa
     default: return SE3_LR_CASE(7);
   }
 #undef SE3_LR_CASE
+#undef SE3_LR_MODE
+}
+
+extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                                   int Kp, int accumulate, float* out, void* stream) {
+  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, nullptr, stream);
+}
+
+// Diagnostic (tools/ only): same launch, and CTA 0 records clock64 stamps of its warp roles into trace[5][64][8].
+extern "C" int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                                     int Kp, int accumulate, float* out, unsigned long long* trace, void* stream) {
+  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, trace, stream);
 }
