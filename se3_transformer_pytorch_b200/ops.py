@@ -73,8 +73,9 @@ def _check(rc):
 class _timed:
     """CUDA-event bracket on the launching stream around one kernel launch (only when PROFILE is enabled)."""
 
-    def __init__(self, name, flops=0, nbytes=0, tag=''):
+    def __init__(self, name, flops=0, nbytes=0, tag='', executed=None):
         self.name, self.flops, self.nbytes, self.tag = name, flops, nbytes, tag
+        self.executed = flops if executed is None else executed
 
     def __enter__(self):
         if PROFILE is not None:
@@ -86,7 +87,7 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.end.record()
-            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes, self.tag))
+            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes, self.tag, self.executed))
         return False
 
 
@@ -338,9 +339,13 @@ def pack_lowrank(Fp, Co, Ci, F, Kp):
 def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
     """Low-rank radial path: U [E,64] fp32 (G V | 1 | 0), w_img from pack_lowrank."""
     _require_cuda(U, w_img, T, out)
-    # executed work: K = Kp instead of 128 for the GEMM, same contraction with T
-    flops = 2 * E * Co * Ci * F * (Kp + P)
-    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, tag=f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}'):
+    # algorithmic work of the reference formulation (SURVEY.md 8d): 2*128 (radial GEMM) + 2P (contraction) per R element;
+    # executed work: the GEMM has K = Kp instead of 128
+    flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
+    executed = 2 * E * Co * Ci * F * (Kp + P)
+    nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
+    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}',
+                                               executed=executed):
         _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
 
 
