@@ -49,6 +49,8 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library next to this file."""
     if not force and is_current():
         return LIB
+    if not force and TAG and 'SE3B200_NVCC_DEFS' not in os.environ and os.path.exists(LIB):
+        return LIB                                   # a tagged experiment variant built elsewhere: load it as it is
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + EXTRA_DEFS
     objs = []

@@ -32,6 +32,13 @@ constexpr uint32_t kLrUnitBytes = 2 * kSubBytes;   // one W tile: [hi 16 KiB | l
 #ifndef SE3_LR_T_STAGES
 #define SE3_LR_T_STAGES 4
 #endif
+// timing experiments only (results are wrong): move only a fraction of each W unit / T stage
+#ifndef SE3_LR_DBG_WDIV
+#define SE3_LR_DBG_WDIV 1
+#endif
+#ifndef SE3_LR_DBG_TDIV
+#define SE3_LR_DBG_TDIV 1
+#endif
 constexpr int kLrWSlots = SE3_LR_W_SLOTS;
 constexpr int kLrTStages = SE3_LR_T_STAGES;
 constexpr int kLrAcc = 3;                          // TMEM accumulator buffers (the MMA -> epilogue -> MMA round trip is long)
@@ -40,6 +47,11 @@ constexpr uint32_t kLrAHi = 384, kLrALo = 416;
 constexpr uint32_t kLrIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // fp16 x fp16 -> fp32, M128 N128
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+#ifdef SE3_LR_DBG_NOLD
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = taddr + i;
+  return;
+#endif
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
@@ -161,7 +173,8 @@ pairwise_lr_kernel(const LrParams prm) {
     if (warp == 0) {
       // ===================== W producer (warp-uniform loop, one elected lane issues) =====================
       const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kLrUnitBytes;
-      constexpr uint32_t kShare = kLrUnitBytes / CSZ;
+      constexpr uint32_t kMove = kLrUnitBytes / SE3_LR_DBG_WDIV;
+      constexpr uint32_t kShare = kMove / CSZ;
       for (int s = 0; s < NIFB; ++s) {
         const int slot = s % kLrWSlots;
         const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
@@ -169,9 +182,9 @@ pairwise_lr_kernel(const LrParams prm) {
         mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
         lr_stamp(prm.trace, 3, s, 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kLrUnitBytes);
+          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kMove);
           if (CSZ == 1) {
-            bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)s * kLrUnitBytes, kLrUnitBytes, bar_w_full + 8 * slot);
+            bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)s * kLrUnitBytes, kMove, bar_w_full + 8 * slot);
           } else {
             bulk_g2s_mc(sW + slot * kLrUnitBytes + crank * kShare, wsrc + (size_t)s * kLrUnitBytes + crank * kShare, kShare,
                         bar_w_full + 8 * slot, kMask);
@@ -189,8 +202,8 @@ pairwise_lr_kernel(const LrParams prm) {
         mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
         lr_stamp(prm.trace, 4, s, 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes);
-          bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes, bar_t_full + 8 * ts);
+          mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes / SE3_LR_DBG_TDIV);
+          bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes / SE3_LR_DBG_TDIV, bar_t_full + 8 * ts);
         }
         __syncwarp();
       }
@@ -220,7 +233,11 @@ pairwise_lr_kernel(const LrParams prm) {
             const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
             for (int k16 = 0; k16 < nk16; ++k16) {
               const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
+#ifndef SE3_LR_DBG_NOMMA
               tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
+#else
+              if (bd == 0x1234u) tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
+#endif
               accum = 1;
             }
           }
@@ -281,6 +298,17 @@ pairwise_lr_kernel(const LrParams prm) {
     const uint32_t tcol0 = tmem_base + t_lane + (uint32_t)(oq * 8);
     const float4* Tsm = reinterpret_cast<const float4*>(base_ptr + (sT - base)) + el;
     auto contract = [&](const uint32_t (&r)[8], const float4 (&t)[PH]) {
+#ifdef SE3_LR_DBG_NOFMA
+      {
+        unsigned long long x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x ^= r[i];
+#pragma unroll
+        for (int h4 = 0; h4 < PH; ++h4) x ^= __float_as_uint(t[h4].x) ^ __float_as_uint(t[h4].w);
+        acc[0][0] ^= x;
+        return;
+      }
+#endif
       float tv[PH * 4];
 #pragma unroll
       for (int h4 = 0; h4 < PH; ++h4) { tv[h4 * 4 + 0] = t[h4].x; tv[h4 * 4 + 1] = t[h4].y; tv[h4 * 4 + 2] = t[h4].z; tv[h4 * 4 + 3] = t[h4].w; }
@@ -294,7 +322,15 @@ pairwise_lr_kernel(const LrParams prm) {
     };
     auto load_t = [&](float4 (&t)[PH], int stage, int ifl) {
 #pragma unroll
-      for (int h4 = 0; h4 < PH; ++h4) t[h4] = Tsm[(size_t)stage * (kTBytes / 16) + (ifl * PH + h4) * 128];
+      for (int h4 = 0; h4 < PH; ++h4) {
+#ifdef SE3_LR_DBG_HALFLDS
+        if (h4 > 0) { t[h4] = make_float4(t[0].y, t[0].x, t[0].w, t[0].z); continue; }
+#endif
+#ifdef SE3_LR_DBG_NOLDS
+        { const float f = __int_as_float(0x3f800000 + stage + ifl); t[h4] = make_float4(f, f, f, f); continue; }
+#endif
+        t[h4] = Tsm[(size_t)stage * (kTBytes / 16) + (ifl * PH + h4) * 128];
+      }
     };
     uint32_t ra[8], rb[8];
     float4 ta[PH], tb[PH];
@@ -308,6 +344,8 @@ pairwise_lr_kernel(const LrParams prm) {
       const int st = s % kLrAcc;
       const int ts = s % kLrTStages;
       const uint32_t tcol = tcol0 + (uint32_t)(st * 128);
+      const int trole = (warp == 4) ? 1 : (warp == 19) ? 2 : -1;
+      if (trole > 0) lr_stamp(prm.trace, trole, s, 0);
       // slot 0
       tmem_ld8(tcol + 32u, rb);
       load_t(tb, ts, 1);
@@ -323,24 +361,29 @@ pairwise_lr_kernel(const LrParams prm) {
       load_t(tb, ts, 3);
       contract(ra, ta);
       tmem_ld_wait();
+      if (trole > 0) lr_stamp(prm.trace, trole, s, 1);
       // every accumulator column of this step is in registers: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
+      if (trole > 0) lr_stamp(prm.trace, trole, s, 2);
       // slot 3, with slot 0 of the next step in flight
       const bool more = s + 1 < NIFB;
       if (more) {
         const int s1 = s + 1;
         mbar_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
         tc_fence_after();
+        if (trole > 0) lr_stamp(prm.trace, trole, s, 3);
         tmem_ld8(tcol0 + (uint32_t)((s1 % kLrAcc) * 128), ra);
         mbar_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
+        if (trole > 0) lr_stamp(prm.trace, trole, s, 4);
         load_t(ta, s1 % kLrTStages, 0);
       }
       contract(rb, tb);
       if (more) tmem_ld_wait();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
+      if (trole > 0) lr_stamp(prm.trace, trole, s, 5);
     }
     } else {
     // The step loop is software pipelined in batches of G (i,f) slots (8 accumulator columns each): while the current
@@ -557,7 +600,7 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
   prm.trace = trace;
   prm.stagger = lr_env_int("SE3B200_LR_STAGGER", 0);
   const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
-  prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 2));
+  prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 4));
   prm.band_m = std::max(1, 148 / (csz * prm.band_o));
   cudaStream_t s = as_stream(stream);
   const int mode_hi = lr_env_int("SE3B200_LR_MODE_HI", 0), mode_lo = lr_env_int("SE3B200_LR_MODE_LO", 0);
