@@ -81,7 +81,7 @@ struct LrParams {
   const float* T;
   float* out;
   int64_t E;
-  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, stagger;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, mma_warps;
   unsigned long long* trace;   // diagnostic: per-role clock64 stamps of CTA 0 ([5 roles][64 steps][8 events]) or nullptr
 };
 
@@ -89,9 +89,9 @@ __device__ __forceinline__ void lr_stamp(unsigned long long* trace, int role, in
   if (trace != nullptr && blockIdx.x == 0 && step < 64 && (threadIdx.x & 31) == 0) trace[(role * 64 + step) * 8 + ev] = clock64();
 }
 
-// MODE selects the epilogue pipelining: 0 = one (i,f) slot ahead (best for P >= 5), 1 = two-slot batches, 2 = whole steps
-// (best for P <= 3).
-template <int P, int CSZ, int MODE>
+// TRACE builds the diagnostic variant whose CTA 0 records clock64 stamps (tools/trace_lr.py); the production kernel has none
+// (the stamps cost ~5 % even when switched off at run time, measured).
+template <int P, int CSZ, bool TRACE>
 __global__ void __launch_bounds__(kLrThreads, 1)
 pairwise_lr_kernel(const LrParams prm) {
   const float* __restrict__ U = prm.U;
@@ -178,9 +178,9 @@ pairwise_lr_kernel(const LrParams prm) {
       for (int s = 0; s < NIFB; ++s) {
         const int slot = s % kLrWSlots;
         const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
-        lr_stamp(prm.trace, 3, s, 0);
+        if constexpr (TRACE) lr_stamp(prm.trace, 3, s, 0);
         mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
-        lr_stamp(prm.trace, 3, s, 1);
+        if constexpr (TRACE) lr_stamp(prm.trace, 3, s, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kMove);
           if (CSZ == 1) {
@@ -198,29 +198,34 @@ pairwise_lr_kernel(const LrParams prm) {
       for (int s = 0; s < NIFB; ++s) {
         const int ts = s % kLrTStages;
         const uint32_t tph = (uint32_t)(s / kLrTStages) & 1u;
-        lr_stamp(prm.trace, 4, s, 0);
+        if constexpr (TRACE) lr_stamp(prm.trace, 4, s, 0);
         mbar_wait(bar_t_empty + 8 * ts, tph ^ 1u);
-        lr_stamp(prm.trace, 4, s, 1);
+        if constexpr (TRACE) lr_stamp(prm.trace, 4, s, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_t_full + 8 * ts, kTBytes / SE3_LR_DBG_TDIV);
           bulk_g2s(sT + ts * kTBytes, tsrc + (size_t)s * kTBytes, kTBytes / SE3_LR_DBG_TDIV, bar_t_full + 8 * ts);
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    } else if (warp == 1 || (warp == 3 && prm.mma_warps == 2)) {
+      // ===================== MMA issuer(s) (warp-uniform loop, one elected lane issues) =====================
+      // One issuing warp spends ~600-900 cycles per step on its own serial chain (two mbarrier waits, the MMA issue, two
+      // commits: measured with tools/trace_lr.py), which bounds the P <= 3 pairs; with two issuers, warp 1 takes the even
+      // steps and warp 3 the odd ones.  Steps use different accumulator buffers, and every hand-off is an mbarrier, so the
+      // order in which the two warps reach the tensor pipe does not matter.
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
-      for (int s = 0; s < NIFB; ++s) {
+      const int s_first = (warp == 3) ? 1 : 0, s_stride = prm.mma_warps;
+      for (int s = s_first; s < NIFB; s += s_stride) {
         const int st = s % kLrAcc;
         const uint32_t ph = (uint32_t)(s / kLrAcc) & 1u;
         const int slot = s % kLrWSlots;
         const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
-        lr_stamp(prm.trace, 0, s, 0);
+        if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 0);
         mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
-        lr_stamp(prm.trace, 0, s, 1);
+        if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 1);
         mbar_wait(bar_w_full + 8 * slot, wph);
-        lr_stamp(prm.trace, 0, s, 2);
+        if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)st * 128u;
         const uint32_t wbase = sW + slot * kLrUnitBytes;
@@ -246,7 +251,7 @@ pairwise_lr_kernel(const LrParams prm) {
           tc_commit(bar_tm_full + 8 * st);
         }
         __syncwarp();
-        lr_stamp(prm.trace, 0, s, 4);
+        if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 4);
       }
     }
   } else {
@@ -291,7 +296,7 @@ pairwise_lr_kernel(const LrParams prm) {
 #pragma unroll
       for (int p = 0; p < P; ++p) acc[a][p] = 0ull;
 
-    if constexpr (MODE == 0) {
+    {
     // The step loop is software pipelined at the granularity of one (i,f) slot (8 accumulator columns, PH T quads):
     // while slot c is contracted, the tcgen05.ld and the LDS of slot c+1 are in flight (tcgen05.wait::ld waits for every
     // outstanding load, so it is placed after the FMAs of the current slot).
@@ -340,12 +345,13 @@ pairwise_lr_kernel(const LrParams prm) {
     mbar_wait(bar_t_full, 0);
     load_t(ta, 0, 0);
     tmem_ld_wait();
+    // running ring indices / phase parities of the current step (no div/mod in the loop)
+    int st = 0, ts = 0;
+    uint32_t ph_acc = 0, ph_t = 0;
     for (int s = 0; s < NIFB; ++s) {
-      const int st = s % kLrAcc;
-      const int ts = s % kLrTStages;
       const uint32_t tcol = tcol0 + (uint32_t)(st * 128);
       const int trole = (warp == 4) ? 1 : (warp == 19) ? 2 : -1;
-      if (trole > 0) lr_stamp(prm.trace, trole, s, 0);
+      if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 0);
       // slot 0
       tmem_ld8(tcol + 32u, rb);
       load_t(tb, ts, 1);
@@ -361,138 +367,33 @@ pairwise_lr_kernel(const LrParams prm) {
       load_t(tb, ts, 3);
       contract(ra, ta);
       tmem_ld_wait();
-      if (trole > 0) lr_stamp(prm.trace, trole, s, 1);
+      if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 1);
       // every accumulator column of this step is in registers: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
-      if (trole > 0) lr_stamp(prm.trace, trole, s, 2);
+      if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 2);
+      int st1 = st + 1, ts1 = ts + 1;
+      uint32_t pa1 = ph_acc, pt1 = ph_t;
+      if (st1 == kLrAcc) { st1 = 0; pa1 ^= 1u; }
+      if (ts1 == kLrTStages) { ts1 = 0; pt1 ^= 1u; }
       // slot 3, with slot 0 of the next step in flight
       const bool more = s + 1 < NIFB;
       if (more) {
-        const int s1 = s + 1;
-        mbar_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
+        mbar_wait(bar_tm_full + 8 * st1, pa1);
         tc_fence_after();
-        if (trole > 0) lr_stamp(prm.trace, trole, s, 3);
-        tmem_ld8(tcol0 + (uint32_t)((s1 % kLrAcc) * 128), ra);
-        mbar_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
-        if (trole > 0) lr_stamp(prm.trace, trole, s, 4);
-        load_t(ta, s1 % kLrTStages, 0);
+        if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 3);
+        tmem_ld8(tcol0 + (uint32_t)(st1 * 128), ra);
+        mbar_wait(bar_t_full + 8 * ts1, pt1);
+        if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 4);
+        load_t(ta, ts1, 0);
       }
       contract(rb, tb);
       if (more) tmem_ld_wait();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
-      if (trole > 0) lr_stamp(prm.trace, trole, s, 5);
-    }
-    } else {
-    // The step loop is software pipelined in batches of G (i,f) slots (8 accumulator columns each): while the current
-    // batch is contracted, the tcgen05.ld of the next batch is in flight.  tcgen05.wait::ld waits for every outstanding
-    // load, so it sits after the FMAs of the current batch; G is chosen so that those FMAs cover the TMEM latency:
-    // G = 2 for P >= 5 (register budget 104: 56 accumulators + 2 x 16 staging), G = 4 (a whole step) for P <= 3.
-    constexpr int G = (MODE == 1) ? 2 : 4;
-    const uint32_t tcol0 = tmem_base + t_lane + (uint32_t)(oq * 8);
-    const float4* Tsm = reinterpret_cast<const float4*>(base_ptr + (sT - base)) + el;
-    auto contract = [&](const uint32_t* r, int stage, int ifl) {          // one slot: 8 columns x P
-      float tv[PH * 4];
-#pragma unroll
-      for (int h4 = 0; h4 < PH; ++h4) {
-        const float4 t4 = Tsm[(size_t)stage * (kTBytes / 16) + (ifl * PH + h4) * 128];
-        tv[h4 * 4 + 0] = t4.x; tv[h4 * 4 + 1] = t4.y; tv[h4 * 4 + 2] = t4.z; tv[h4 * 4 + 3] = t4.w;
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const unsigned long long t2 = pack2(tv[p], tv[p]);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          acc[a][p] = fma2(pack2(__uint_as_float(r[2 * a]), __uint_as_float(r[2 * a + 1])), t2, acc[a][p]);
-      }
-    };
-    auto issue = [&](uint32_t (&r)[G][8], int step, int first_slot) {     // G tcgen05.ld of 8 columns each
-      const uint32_t tcol = tcol0 + (uint32_t)((step % kLrAcc) * 128 + first_slot * 32);
-#pragma unroll
-      for (int j = 0; j < G; ++j) tmem_ld8(tcol + (uint32_t)(j * 32), r[j]);
-    };
-    auto wait_acc = [&](int step) {
-      mbar_wait(bar_tm_full + 8 * (step % kLrAcc), (uint32_t)(step / kLrAcc) & 1u);
-      tc_fence_after();
-    };
-    auto wait_t = [&](int step) { mbar_wait(bar_t_full + 8 * (step % kLrTStages), (uint32_t)(step / kLrTStages) & 1u); };
-    auto release_acc = [&](int step) {                                      // all loads of `step` have completed
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tm_empty + 8 * (step % kLrAcc));
-    };
-    auto release_t = [&](int step) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_t_empty + 8 * (step % kLrTStages));
-    };
-    // De-phase the four epilogue warps of each SM sub-partition (same q, oq = 0..3) by a quarter of a step: every warp
-    // alternates an FMA phase with a synchronisation phase (tcgen05.ld latency, mbarrier round trips); left in lockstep
-    // they all sit in the synchronisation phase together and the FMA pipe idles half of the time (measured).
-    if (prm.stagger > 0 && oq > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)oq * prm.stagger) {
-      }
-    }
-    uint32_t ra[G][8], rb[G][8];
-    wait_acc(0);
-    issue(ra, 0, 0);
-    tmem_ld_wait();
-    if constexpr (G == 2) {
-      wait_t(0);
-      for (int s = 0; s < NIFB; ++s) {
-        const int ts = s % kLrTStages;
-        const bool more = s + 1 < NIFB;
-        const int s1 = s + 1;
-        issue(rb, s, 2);                        // slots 2,3 of this step
-        // probe the next step's barriers now and consume the answers after the FMAs: an mbarrier try_wait costs ~100
-        // cycles of latency even when the phase has long completed
-        uint32_t acc_ok = 1, t_ok = 1;
-        if (more) {
-          acc_ok = mbar_try_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
-          t_ok = mbar_try_wait(bar_t_full + 8 * (s1 % kLrTStages), (uint32_t)(s1 / kLrTStages) & 1u);
-        }
-        contract(ra[0], ts, 0);
-        contract(ra[1], ts, 1);
-        tmem_ld_wait();
-        release_acc(s);
-        if (more) {
-          if (!acc_ok) mbar_wait(bar_tm_full + 8 * (s1 % kLrAcc), (uint32_t)(s1 / kLrAcc) & 1u);
-          tc_fence_after();
-          issue(ra, s1, 0);
-        }
-        contract(rb[0], ts, 2);
-        contract(rb[1], ts, 3);
-        if (more) tmem_ld_wait();
-        release_t(s);
-        if (more && !t_ok) wait_t(s1);
-      }
-    } else {
-      // whole-step batches: ra holds the current step, rb receives the next one (roles swap every step)
-      if (NIFB == 1) release_acc(0);
-      for (int s = 0; s < NIFB; s += 2) {
-        {
-          const bool more = s + 1 < NIFB;
-          if (more) { wait_acc(s + 1); issue(rb, s + 1, 0); }
-          if (s == 0 && more) release_acc(0);   // step 0 was loaded in the prologue
-          wait_t(s);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) contract(ra[j], s % kLrTStages, j);
-          if (more) { tmem_ld_wait(); release_acc(s + 1); }
-          release_t(s);
-        }
-        if (s + 1 < NIFB) {
-          const int s1 = s + 1;
-          const bool more = s1 + 1 < NIFB;
-          if (more) { wait_acc(s1 + 1); issue(ra, s1 + 1, 0); }
-          wait_t(s1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) contract(rb[j], s1 % kLrTStages, j);
-          if (more) { tmem_ld_wait(); release_acc(s1 + 1); }
-          release_t(s1);
-        }
-      }
+      if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 5);
+      st = st1; ts = ts1; ph_acc = pa1; ph_t = pt1;
     }
     }
     // write out[e, ob*32 + oq*8 + (0..7), 0..P)
@@ -529,10 +430,10 @@ static size_t lr_smem_bytes() {
   return 1024 + kLrWSlots * kLrUnitBytes + kLrTStages * (PH * 8192u) + 256;
 }
 
-template <int P, int CSZ, int MODE>
+template <int P, int CSZ, bool TRACE>
 static int launch_lr(const LrParams& prm, cudaStream_t s) {
   const size_t smem = lr_smem_bytes<P>();
-  auto kern = pairwise_lr_kernel<P, CSZ, MODE>;
+  auto kern = pairwise_lr_kernel<P, CSZ, TRACE>;
   SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_mg = (prm.n_mt + CSZ - 1) / CSZ;
   cudaLaunchConfig_t cfg = {};
@@ -598,14 +499,12 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
   prm.trace = trace;
-  prm.stagger = lr_env_int("SE3B200_LR_STAGGER", 0);
-  const int csz = lr_env_int("SE3B200_LR_CLUSTER", 2) == 1 ? 1 : 2;
+  prm.mma_warps = lr_env_int("SE3B200_LR_MMA_WARPS", 2) == 1 ? 1 : 2;
+  const int csz = (trace == nullptr && lr_env_int("SE3B200_LR_CLUSTER", 2) == 1) ? 1 : 2;
   prm.band_o = std::max(1, lr_env_int("SE3B200_LR_BANDO", 4));
   prm.band_m = std::max(1, 148 / (csz * prm.band_o));
   cudaStream_t s = as_stream(stream);
-  const int mode_hi = lr_env_int("SE3B200_LR_MODE_HI", 0), mode_lo = lr_env_int("SE3B200_LR_MODE_LO", 0);
-#define SE3_LR_MODE(PP, M) (csz == 1 ? launch_lr<PP, 1, M>(prm, s) : launch_lr<PP, 2, M>(prm, s))
-#define SE3_LR_CASE(PP) ((PP >= 5 ? mode_hi : mode_lo) == 0 ? SE3_LR_MODE(PP, 0) : (PP >= 5 ? mode_hi : mode_lo) == 1 ? SE3_LR_MODE(PP, 1) : SE3_LR_MODE(PP, 2))
+#define SE3_LR_CASE(PP) (trace != nullptr ? launch_lr<PP, 2, true>(prm, s) : csz == 1 ? launch_lr<PP, 1, false>(prm, s) : launch_lr<PP, 2, false>(prm, s))
   switch (P) {
     case 1: return SE3_LR_CASE(1);
     case 3: return SE3_LR_CASE(3);
@@ -613,7 +512,6 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
     default: return SE3_LR_CASE(7);
   }
 #undef SE3_LR_CASE
-#undef SE3_LR_MODE
 }
 
 extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,

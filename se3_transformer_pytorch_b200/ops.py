@@ -349,10 +349,19 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
         _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
 
 
-def lowrank_basis(G64, tol=2e-7, ranks=(15, 31, 47, 63)):
+# max-abs residual of the radial basis relative to max|G|.  The fp32 trunk itself carries ~6e-7..1e-6 of rounding noise
+# against float64, so 1e-6 keeps the truncation below what fp32 can resolve; at the headline width (depth-2 slice of cfg2)
+# the output differs from the fp32 SIMT path by 1.6e-5 with 1e-6 and by 1.5e-5 with 2e-7 or with the direct K = 128 kernel
+# (tools/lr_tol_check.py).  With 1e-6, 96 % of the cfg2 pairs need rank <= 15 (K = 16) instead of 26 % with 2e-7.
+LOWRANK_TOL = 1e-6
+
+
+def lowrank_basis(G64, tol=None, ranks=(15, 31, 47, 63)):
     """Orthonormal basis of the row space of G64 [S, 128] (float64 samples of a radial trunk along its input curve):
     returns (r, V [128, r] float64) for the smallest listed rank with  max|G - (G V) V^T| <= tol * max|G|, else None.
     QR + SVD of the triangular factor (no Gram matrix, so the small singular directions stay accurate)."""
+    if tol is None:
+        tol = float(os.environ.get('SE3B200_LOWRANK_TOL', LOWRANK_TOL))
     _, Rm = torch.linalg.qr(G64)
     _, _, Vh = torch.linalg.svd(Rm)
     gmax = float(G64.abs().max())

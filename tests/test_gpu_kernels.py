@@ -253,7 +253,7 @@ def test_pairwise_lowrank_matches_fp64(r, P, di, do):
 
 
 def test_lowrank_basis_of_radial_trunk():
-    """Distance-only radial trunks are numerically low rank: a basis of rank <= 31 reproduces the float64 curve to 2e-7,
+    """Distance-only radial trunks are numerically low rank: a basis of rank <= 31 reproduces the float64 curve to 1e-6 (ops.LOWRANK_TOL),
     and the fp32 kernel outputs at unseen distances stay within fp32 noise of that subspace."""
     from se3_transformer_pytorch_b200 import ops
     from se3_transformer_pytorch_b200.model import RadialFunc
