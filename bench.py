@@ -242,6 +242,7 @@ def run_ours(args, wl, rank, local_rank, world):
     model.pack_weights(free_master=True, max_distance=16.0 if lowrank else None)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
+    weights_gb = torch.cuda.memory_allocated(dev) / 1e9
     b, n, dim = wl['b'], wl['n'], wl['ctor']['dim']
     fwd_kw = wl.get('fwd', {})
     g = torch.Generator().manual_seed(99 + rank)
@@ -379,7 +380,7 @@ def run_ours(args, wl, rank, local_rank, world):
         'data': 'synthetic',
         'config': {'workload': args.workload, **wl['ctor'], 'batch_per_gpu': b, 'global_batch': b * world, 'n_points': n,
                    'parallelism': f'dp{world} (batch sharded, replicated weights, one all-gather of outputs)',
-                   'cache': 'inputs larger than L2: every step streams the 77 GB weight image', 'random_init': True, 'cuda_graph': bool(args.cuda_graph), 'lowrank_radial': bool(lowrank),
+                   'cache': f'inputs larger than L2: every step streams the {weights_gb:.1f} GB of weight images and the per-layer T / K / V tensors (several GB each)', 'weights_resident_gb': weights_gb, 'random_init': True, 'cuda_graph': bool(args.cuda_graph), 'lowrank_radial': bool(lowrank),
                    'flops_per_cloud': forward_flops(wl) / b, 'model_build_s': t_build},
         'e2e': {'value': e2e, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,

@@ -107,10 +107,17 @@ int se3_pairwise_tc_debug(const float* g, const void* w_img, const float* T, int
  *   Fp [Co*Ci*F, Kp] fp32: columns 0..r-1 = W3 V, column r = b3, remaining 0;  Kp = 16*ceil((r+1)/16) <= 64
  * se3_pack_lowrank images Fp for the tensor cores (se3_lowrank_image_bytes bytes) and se3_pairwise_lr_fwd evaluates the
  * same contraction as se3_pairwise_tc_fwd with K = Kp instead of 128 (bias folded into the GEMM). */
-int64_t se3_lowrank_image_bytes(int Co, int Ci, int F);
+int64_t se3_lowrank_image_bytes(int Co, int Ci, int F, int Kp);
 int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, void* image, void* stream);
 int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                         int Kp, int accumulate, float* out, void* stream);
+
+/* Basis fold of the input-side contraction (pairs with 2 l_in + 1 = Q < P = 2 l_out + 1; S:336-343, 251 reassociated):
+ *   out[e,o,p] (+)= sum_{f,q} basis_pair[e,p,q,f] * S[f,e,o,q]
+ * where S[f] [E,Co,Q] = se3_pairwise_lr_fwd with F := 1, P := Q, T := the gathered neighbour features in tile layout
+ * (se3_tbuild_fwd with an identity basis) and the image of frequency f's rows of Fp.  basis_pair: [E,P,Q,F] of these E edges. */
+int se3_fold_basis_fwd(const float* S, const float* basis_pair, int64_t E, int Co, int P, int Q, int F, int accumulate,
+                       float* out, void* stream);
 
 /* Diagnostic for tools/: as se3_pairwise_lr_fwd; CTA 0 writes clock64 stamps of its warp roles to trace[5][64][8] (u64). */
 int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,

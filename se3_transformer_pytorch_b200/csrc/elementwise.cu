@@ -27,7 +27,63 @@ norm_kernel(const float* __restrict__ x, const float* __restrict__ scale, int64_
   for (int m = 0; m < M; ++m) op[m] = t * (v[m] / nrm);
 }
 
+// Basis fold of the input-side contraction.  For a degree pair with 2 l_in + 1 = Q < P = 2 l_out + 1 the
+// reference's per-edge product  out[e,o,p] = sum_{i,f} R[e,o,i,f] * (sum_q B[e,p,q,f] x[j(e),i,q])  (S:336-343, 251) is
+// evaluated as  S[f,e,o,q] = sum_i R[e,o,i,f] x[j(e),i,q]  by the fused pairwise kernel (Q instead of P FMAs per R
+// element) followed by this fold:  out[e,o,p] (+)= sum_{f,q} B[e,p,q,f] S[f,e,o,q].
+// One thread per (edge, channel); the P*Q*F basis values of the block's edges are staged in shared memory.
+constexpr int kFoldThreads = 256;
+constexpr int kFoldMaxB = 7 * 7 * 7;
+
+__global__ void __launch_bounds__(kFoldThreads)
+fold_basis_kernel(const float* __restrict__ S, const float* __restrict__ basis, int64_t E, int Co, int P, int Q, int F,
+                  int accumulate, float* __restrict__ out) {
+  extern __shared__ float sB[];                       // [edges of this block][P*Q*F]
+  const int64_t first = (int64_t)blockIdx.x * kFoldThreads;
+  const int64_t e_first = first / Co;
+  const int64_t last = min(first + kFoldThreads, E * Co) - 1;
+  const int n_edges = (int)(last / Co - e_first) + 1;
+  const int nb = P * Q * F;
+  for (int t = threadIdx.x; t < n_edges * nb; t += kFoldThreads) sB[t] = basis[e_first * nb + t];
+  __syncthreads();
+  const int64_t idx = first + threadIdx.x;
+  if (idx >= E * Co) return;
+  const int64_t e = idx / Co;
+  const float* b = sB + (e - e_first) * nb;           // [p][q][f]
+  float acc[7];
+#pragma unroll
+  for (int p = 0; p < 7; ++p) acc[p] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float* sp = S + ((size_t)f * E * Co + idx) * Q;
+    for (int q = 0; q < Q; ++q) {
+      const float sv = sp[q];
+#pragma unroll
+      for (int p = 0; p < 7; ++p)
+        if (p < P) acc[p] = fmaf(b[(p * Q + q) * F + f], sv, acc[p]);
+    }
+  }
+  float* op = out + idx * P;
+#pragma unroll
+  for (int p = 0; p < 7; ++p)
+    if (p < P) op[p] = accumulate ? op[p] + acc[p] : acc[p];
+}
+
 }  // namespace se3
+
+extern "C" int se3_fold_basis_fwd(const float* S, const float* basis_pair, int64_t E, int Co, int P, int Q, int F, int accumulate,
+                                  float* out, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(E > 0 && Co > 0, "se3_fold_basis_fwd: bad sizes");
+  SE3_REQUIRE(P >= 1 && P <= 7 && Q >= 1 && Q <= 7 && F >= 1 && F <= 7, "se3_fold_basis_fwd: P=%d Q=%d F=%d unsupported (degrees <= 3)", P, Q, F);
+  const int64_t total = E * Co;
+  const unsigned blocks = (unsigned)ceil_div(total, (int64_t)kFoldThreads);
+  const int max_edges = kFoldThreads / Co + 2;
+  const size_t smem = (size_t)max_edges * P * Q * F * sizeof(float);
+  SE3_REQUIRE(smem <= 48 * 1024, "se3_fold_basis_fwd: Co=%d too small for the staging buffer", Co);
+  fold_basis_kernel<<<blocks, kFoldThreads, smem, as_stream(stream)>>>(S, basis_pair, E, Co, P, Q, F, accumulate, out);
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
 
 extern "C" int se3_norm_fwd(const float* x, const float* scale, int64_t rows, int C, int M, float eps, int use_gelu, float* out,
                             void* stream) {

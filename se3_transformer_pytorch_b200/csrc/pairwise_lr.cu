@@ -57,16 +57,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr));
 }
 
-// F'' image packer: Fp fp32 [Co*Ci*F, Kp] (columns 0..r-1 = W3 V, column r = b3, rest 0) -> per (32-channel block,
-// 4-(i,f) block) tile [hi 128 x 64 | lo 128 x 64] fp16, SW128, row = if_local*32 + o_local
-__global__ void pack_lr_kernel(const float* __restrict__ Fp, int Co, int CiF, int NIFB, int Kp, uint8_t* __restrict__ img) {
+// F'' image packer: Fp fp32 [Co*Ci*F, Kp] (columns 0..r-1 = W3 V, column r = b3, rest 0) -> per 32-channel block a row of
+// 32 KiB units [hi 128 x 64 | lo 128 x 64] fp16, SW128, row = if_local*32 + o_local.  A unit holds spu = 64 / Kp (Kp = 16,
+// 32: 4, 2; else 1) consecutive (i,f) steps side by side along K: step j of the unit occupies K columns [j*Kp, (j+1)*Kp),
+// so the streamed bytes per step are what the MMAs read (K = Kp), not a K = 64 padded tile.
+__global__ void pack_lr_kernel(const float* __restrict__ Fp, int Co, int CiF, int NU, int Kp, int spu, uint8_t* __restrict__ img) {
   const int64_t tile = blockIdx.x;
-  const int ob = (int)(tile / NIFB), ifb = (int)(tile % NIFB);
+  const int ob = (int)(tile / NU), un = (int)(tile % NU);
   uint8_t* dst = img + (size_t)tile * kLrUnitBytes;
   for (int t = threadIdx.x; t < 128 * 64; t += blockDim.x) {
     const int r = t >> 6, k = t & 63;
+    const int sub = k / Kp, kk = k - sub * Kp;
+    const int ifb = un * spu + sub;
     const int o = ob * SE3_TILE_O + (r & 31), ifx = ifb * SE3_TILE_IF + (r >> 5);
-    const float w = (ifx < CiF && k < Kp) ? Fp[((size_t)o * CiF + ifx) * Kp + k] : 0.f;
+    const float w = (sub < spu && ifx < CiF) ? Fp[((size_t)o * CiF + ifx) * Kp + kk] : 0.f;
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
     const uint32_t off = sw128_off(r, k);
@@ -75,13 +79,15 @@ __global__ void pack_lr_kernel(const float* __restrict__ Fp, int Co, int CiF, in
   }
 }
 
+__host__ __device__ inline int lr_steps_per_unit(int Kp) { return Kp == 16 ? 4 : Kp == 32 ? 2 : 1; }
+
 struct LrParams {
   const float* U;          // [E, 64] fp32: columns 0..r-1 = G V, column r = 1, rest 0
   const uint8_t* w_img;
   const float* T;
   float* out;
   int64_t E;
-  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, mma_warps;
+  int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, mma_warps, spu, NU;
   unsigned long long* trace;   // diagnostic: per-role clock64 stamps of CTA 0 ([5 roles][64 steps][8 events]) or nullptr
 };
 
@@ -99,7 +105,7 @@ pairwise_lr_kernel(const LrParams prm) {
   const float* __restrict__ T = prm.T;
   float* __restrict__ out = prm.out;
   const int64_t E = prm.E;
-  const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, nk16 = prm.nk16;
+  const int Co = prm.Co, NIFB = prm.NIFB, n_mt = prm.n_mt, n_ob = prm.n_ob, accumulate = prm.accumulate, nk16 = prm.nk16, spu = prm.spu, NU = prm.NU;
   constexpr int PH = (P + 3) / 4;
   constexpr uint32_t kTBytes = PH * 8192u;
   extern __shared__ uint8_t smem_raw[];
@@ -145,7 +151,7 @@ pairwise_lr_kernel(const LrParams prm) {
     mbar_init(bar_a_full, 4);
     for (int s = 0; s < kLrWSlots; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, CSZ);
+      mbar_init(bar_w_empty + 8 * s, CSZ * spu);   // every step of the unit commits once per CTA of the cluster
     }
     for (int s = 0; s < kLrTStages; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
@@ -172,21 +178,21 @@ pairwise_lr_kernel(const LrParams prm) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
       // ===================== W producer (warp-uniform loop, one elected lane issues) =====================
-      const uint8_t* wsrc = w_img + (size_t)ob * NIFB * kLrUnitBytes;
+      const uint8_t* wsrc = w_img + (size_t)ob * NU * kLrUnitBytes;
       constexpr uint32_t kMove = kLrUnitBytes / SE3_LR_DBG_WDIV;
       constexpr uint32_t kShare = kMove / CSZ;
-      for (int s = 0; s < NIFB; ++s) {
-        const int slot = s % kLrWSlots;
-        const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
-        if constexpr (TRACE) lr_stamp(prm.trace, 3, s, 0);
+      for (int u = 0; u < NU; ++u) {
+        const int slot = u % kLrWSlots;
+        const uint32_t wph = (uint32_t)(u / kLrWSlots) & 1u;
+        if constexpr (TRACE) lr_stamp(prm.trace, 3, u, 0);
         mbar_wait(bar_w_empty + 8 * slot, wph ^ 1u);
-        if constexpr (TRACE) lr_stamp(prm.trace, 3, s, 1);
+        if constexpr (TRACE) lr_stamp(prm.trace, 3, u, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kMove);
           if (CSZ == 1) {
-            bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)s * kLrUnitBytes, kMove, bar_w_full + 8 * slot);
+            bulk_g2s(sW + slot * kLrUnitBytes, wsrc + (size_t)u * kLrUnitBytes, kMove, bar_w_full + 8 * slot);
           } else {
-            bulk_g2s_mc(sW + slot * kLrUnitBytes + crank * kShare, wsrc + (size_t)s * kLrUnitBytes + crank * kShare, kShare,
+            bulk_g2s_mc(sW + slot * kLrUnitBytes + crank * kShare, wsrc + (size_t)u * kLrUnitBytes + crank * kShare, kShare,
                         bar_w_full + 8 * slot, kMask);
           }
         }
@@ -219,8 +225,9 @@ pairwise_lr_kernel(const LrParams prm) {
       for (int s = s_first; s < NIFB; s += s_stride) {
         const int st = s % kLrAcc;
         const uint32_t ph = (uint32_t)(s / kLrAcc) & 1u;
-        const int slot = s % kLrWSlots;
-        const uint32_t wph = (uint32_t)(s / kLrWSlots) & 1u;
+        const int un = s / spu, sub = s - un * spu;          // W unit and the K sub-range of this step inside it
+        const int slot = un % kLrWSlots;
+        const uint32_t wph = (uint32_t)(un / kLrWSlots) & 1u;
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 0);
         mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 1);
@@ -237,7 +244,7 @@ pairwise_lr_kernel(const LrParams prm) {
             const uint32_t a_tmem = tmem_base + ((pass == 1) ? kLrALo : kLrAHi);
             const uint32_t b_part = (pass == 2) ? kSubBytes : 0u;
             for (int k16 = 0; k16 < nk16; ++k16) {
-              const uint64_t bd = umma_desc_sw128(wbase + b_part + k16 * 32);
+              const uint64_t bd = umma_desc_sw128(wbase + b_part + (sub * nk16 + k16) * 32);
 #ifndef SE3_LR_DBG_NOMMA
               tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(k16 * 8), bd, kLrIdesc, accum);
 #else
@@ -459,10 +466,11 @@ static int lr_env_int(const char* name, int dflt) {
 
 }  // namespace se3
 
-extern "C" int64_t se3_lowrank_image_bytes(int Co, int Ci, int F) {
-  if (Co <= 0 || Ci <= 0 || F <= 0 || Co % SE3_TILE_O != 0) return -1;
+extern "C" int64_t se3_lowrank_image_bytes(int Co, int Ci, int F, int Kp) {
+  if (Co <= 0 || Ci <= 0 || F <= 0 || Co % SE3_TILE_O != 0 || Kp < 16 || Kp > 64 || Kp % 16 != 0) return -1;
   const int64_t NIFB = se3::ceil_div((int64_t)Ci * F, SE3_TILE_IF);
-  return (int64_t)(Co / SE3_TILE_O) * NIFB * se3::kLrUnitBytes;
+  const int64_t NU = se3::ceil_div(NIFB, (int64_t)se3::lr_steps_per_unit(Kp));
+  return (int64_t)(Co / SE3_TILE_O) * NU * se3::kLrUnitBytes;
 }
 
 extern "C" int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, void* image, void* stream) {
@@ -471,9 +479,11 @@ extern "C" int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, 
   SE3_REQUIRE(Kp >= 16 && Kp <= 64 && Kp % 16 == 0, "se3_pack_lowrank: Kp=%d must be 16, 32, 48 or 64", Kp);
   const int CiF = Ci * F;
   const int NIFB = (int)ceil_div(CiF, SE3_TILE_IF);
-  const int64_t tiles = (int64_t)(Co / SE3_TILE_O) * NIFB;
+  const int spu = lr_steps_per_unit(Kp);
+  const int NU = (int)ceil_div(NIFB, spu);
+  const int64_t tiles = (int64_t)(Co / SE3_TILE_O) * NU;
   SE3_REQUIRE(tiles < 2147483647ll, "se3_pack_lowrank: too many tiles");
-  pack_lr_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(Fp, Co, CiF, NIFB, Kp, reinterpret_cast<uint8_t*>(image));
+  pack_lr_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(Fp, Co, CiF, NU, Kp, spu, reinterpret_cast<uint8_t*>(image));
   SE3_LAUNCH_OK();
   return SE3_OK;
 }
@@ -498,6 +508,8 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
   prm.n_ob = Co / SE3_TILE_O;
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
+  prm.spu = lr_steps_per_unit(Kp);
+  prm.NU = (int)ceil_div((int64_t)prm.NIFB, (int64_t)prm.spu);
   prm.trace = trace;
   prm.mma_warps = lr_env_int("SE3B200_LR_MMA_WARPS", 2) == 1 ? 1 : 2;
   const int csz = (trace == nullptr && lr_env_int("SE3B200_LR_CLUSTER", 2) == 1) ? 1 : 2;

@@ -168,7 +168,7 @@ extern "C" int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* b
   slabs = (int)ceil_div(Ci, ci_per_cta);
   dim3 grid((unsigned)n_mtiles, (unsigned)slabs);
   cudaStream_t st = as_stream(stream);
-  if (P <= 7 && Q <= 7) {
+  if (P <= 7 && Q <= 7 && F == std::min(P, Q)) {        // the register variant has F = 2*min(li,lo)+1 compiled in
 #define SE3_TB(PP, QQ) if (P == PP && Q == QQ) launch_reg<PP, QQ>(grid, st, x, idx, basis_pair, E, tile_begin, n, k, Ci, F, ci_per_cta, T);
     SE3_TB(1, 1) SE3_TB(1, 3) SE3_TB(1, 5) SE3_TB(1, 7) SE3_TB(3, 1) SE3_TB(3, 3) SE3_TB(3, 5) SE3_TB(3, 7)
     SE3_TB(5, 1) SE3_TB(5, 3) SE3_TB(5, 5) SE3_TB(5, 7) SE3_TB(7, 1) SE3_TB(7, 3) SE3_TB(7, 5) SE3_TB(7, 7)

@@ -278,7 +278,15 @@ class ConvSE3(nn.Module):
                 Fp[:, r] = lin.bias
                 Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
                 Vp[:, :r] = V.float()
-                pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=ops.pack_lowrank(Fp, pc.nc_out, pc.nc_in, pc.num_freq, Kp))
+                if input_side(di, do) and pc.num_freq > 1:
+                    # input-side contraction: one image per frequency f (rows (o,i,f) of F'), no combined image
+                    Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp)
+                    imgs = [ops.pack_lowrank(Fv[:, :, f, :].reshape(-1, Kp).contiguous(), pc.nc_out, pc.nc_in, 1, Kp)
+                            for f in range(pc.num_freq)]
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=imgs)
+                else:
+                    img = ops.pack_lowrank(Fp, pc.nc_out, pc.nc_in, pc.num_freq, Kp)
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=img, imgs_f=[img] if pc.num_freq == 1 else None)
                 del Fp
         plan = dict(D=D, pairs=pairs)
         pk['lr'] = plan
@@ -317,6 +325,13 @@ class ConvSE3(nn.Module):
 
     def forward(self, inp, edge_info, rel_dist=None, basis=None):
         return conv_forward([self], inp, edge_info, rel_dist, basis)[0]
+
+
+def input_side(di, do):
+    """Degree pairs evaluated with the input-side contraction on the low-rank path: out = B . (R x) instead of R (B x).
+    The fused kernel then spends 2 l_in + 1 instead of 2 l_out + 1 FMAs per radial weight; worth it for l_in <= 1 < l_out
+    and for l_in = 0 (measured: (0,3) 7.7 -> 2.6 ms, (1,3) 19.3 -> ~11.4 ms at cfg2 widths)."""
+    return di < do and di <= 1 and not os.environ.get('SE3B200_NO_INPUT_SIDE')
 
 
 def conv_forward(convs, inp, edge_info, rel_dist, basis):
@@ -358,7 +373,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 res = (g[pi] - U[pi] @ pp['V'].t()).abs().max() / g[pi].abs().max().clamp(min=1e-30)
                 worst = torch.maximum(worst, res)
                 U[pi, :, pp['r']] = 1.0
-                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'])
+                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'))
             if float(worst) > conv.LR_RUNTIME_TOL:
                 # the fp32 trunk outputs of this forward leave the cached subspace (distances beyond the plan's range)
                 if conv.free_master:
@@ -377,17 +392,33 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         tc = min(tiles_per_chunk, n_tiles - t0)
         e0 = t0 * ops.TILE_E
         ec = min(E - e0, tc * ops.TILE_E)
+        gathered = {}                            # degree_in -> neighbour features of this chunk in tile layout
         for do, mo in c0.fiber_out:
             P = to_order(do)
             first = True
             for di, mi in c0.fiber_in:
                 Fq = to_order(min(di, do))
-                workspace = ops.tbuild(inp[str(di)], idx, bpairs[(di, do)], di, do, t0, tc, out=workspace)
+                Q = to_order(di)
+                in_side = [input_side(di, do) and (di, do) in st['lr'] and st['lr'][(di, do)]['imgs_f'] is not None for st in states]
+                if any(in_side) and di not in gathered:
+                    gathered[di] = ops.gather_tiles(inp[str(di)], idx, t0, tc)
+                if not all(in_side):
+                    workspace = ops.tbuild(inp[str(di)], idx, bpairs[(di, do)], di, do, t0, tc, out=workspace)
                 pi = c0.pairs.index((di, do))
-                for st in states:
+                for st, ins in zip(states, in_side):
                     conv = st['conv']
                     out = st['outs'][do][e0:e0 + ec]
-                    if (di, do) in st['lr']:
+                    if ins:
+                        # S[f,e,o,q] = sum_i R[e,o,i,f] x[j(e),i,q], then out[e,o,p] (+)= sum_{f,q} B[e,p,q,f] S[f,e,o,q]
+                        lrp = st['lr'][(di, do)]
+                        S = torch.empty((Fq, ec, mo, Q), dtype=torch.float32, device=dev)
+                        for f in range(Fq):
+                            ops.pairwise_lr(lrp['U'][e0:e0 + ec], lrp['imgs_f'][f], gathered[di], ec, mo, mi, 1, Q, lrp['Kp'], S[f],
+                                            accumulate=False, alg_P=P)
+                        ops.fold_basis(S, bpairs[(di, do)][e0 * P * Q * Fq:(e0 + ec) * P * Q * Fq], ec, mo, P, Q, Fq, out,
+                                       accumulate=not first)
+                        del S
+                    elif (di, do) in st['lr']:
                         lrp = st['lr'][(di, do)]
                         ops.pairwise_lr(lrp['U'][e0:e0 + ec], lrp['img'], workspace, ec, mo, mi, Fq, P, lrp['Kp'], out,
                                         accumulate=not first)

@@ -32,10 +32,11 @@ _SIGNATURES = {
     'se3_pack_w3': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_pairwise_tc_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p]),
     'se3_pairwise_tc_debug': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
-    'se3_lowrank_image_bytes': (c_int64, [c_int, c_int, c_int]),
+    'se3_lowrank_image_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
     'se3_pack_lowrank': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_pairwise_lr_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_void_p]),
     'se3_pairwise_lr_trace': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_void_p, c_void_p]),
+    'se3_fold_basis_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
@@ -290,6 +291,43 @@ def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=N
     return out
 
 
+_IDENTITY_BASIS = {}
+
+
+def gather_tiles(x, idx, tile_begin=0, tile_count=None, out=None):
+    """Neighbour features in the T tile layout: X[e,i,q] = x[b, idx[e], i, q] (se3_tbuild_fwd with an identity basis,
+    P := Q, F := 1); the right-hand operand of the input-side contraction."""
+    _require_cuda(x, idx)
+    x = _f32(x)
+    b, n, Ci, Q = x.shape
+    k = idx.shape[-1]
+    E = b * n * k
+    key = (E, Q, x.device)
+    if key not in _IDENTITY_BASIS:
+        _IDENTITY_BASIS.clear()
+        _IDENTITY_BASIS[key] = torch.eye(Q, dtype=torch.float32, device=x.device).repeat(E, 1, 1).reshape(-1).contiguous()
+    eye = _IDENTITY_BASIS[key]
+    n_tiles = (E + TILE_E - 1) // TILE_E
+    if tile_count is None:
+        tile_count = n_tiles - tile_begin
+    numel = t_numel(tile_count, Ci, 1, Q)
+    if out is None or out.numel() < numel:
+        out = torch.empty(numel, dtype=torch.float32, device=x.device)
+    nbytes = 4 * (numel + E * Ci * Q) + 8 * E
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * Q * Q, nbytes=nbytes):
+        _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(eye), b, n, k, Ci, Q, Q, 1, tile_begin, tile_count, _p(out), _stream()))
+    return out
+
+
+def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate):
+    """out [E,Co,P] (+)= sum_{f,q} basis_pair[e,p,q,f] S[f,e,o,q]; S [F,E,Co,Q], basis_pair the [E,P,Q,F] rows of these edges."""
+    _require_cuda(S, basis_pair, out)
+    assert S.is_contiguous() and basis_pair.is_contiguous() and out.is_contiguous()
+    nbytes = 4 * (S.numel() + basis_pair.numel() + out.numel() * (2 if accumulate else 1))
+    with torch.cuda.device(out.device), _timed('fold_basis', flops=2 * E * Co * P * Q * F, nbytes=nbytes):
+        _check(lib().se3_fold_basis_fwd(_p(S), _p(basis_pair), E, Co, P, Q, F, int(accumulate), _p(out), _stream()))
+
+
 def pairwise_simt(g, W3, b3, T, E, Co, Ci, F, P, out, accumulate):
     _require_cuda(g, W3, b3, T, out)
     with torch.cuda.device(out.device), _timed('pairwise_simt', flops=2 * E * Co * Ci * F * (RADIAL_MID + P)):
@@ -327,7 +365,7 @@ def pairwise_tc(g, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
 def pack_lowrank(Fp, Co, Ci, F, Kp):
     """Fp [Co*Ci*F, Kp] fp32 (W3 V | b3 | 0) -> tensor-core operand image for pairwise_lr."""
     _require_cuda(Fp)
-    nbytes = lib().se3_lowrank_image_bytes(Co, Ci, F)
+    nbytes = lib().se3_lowrank_image_bytes(Co, Ci, F, Kp)
     if nbytes < 0:
         raise RuntimeError(f'pack_lowrank: unsupported shape Co={Co} Ci={Ci} F={F}')
     img = torch.empty(nbytes, dtype=torch.uint8, device=Fp.device)
@@ -336,16 +374,17 @@ def pack_lowrank(Fp, Co, Ci, F, Kp):
     return img
 
 
-def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate):
+def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None):
     """Low-rank radial path: U [E,64] fp32 (G V | 1 | 0), w_img from pack_lowrank."""
     _require_cuda(U, w_img, T, out)
     # algorithmic work of the reference formulation (SURVEY.md 8d): 2*128 (radial GEMM) + 2P (contraction) per R element;
     # executed work: the GEMM has K = Kp instead of 128
-    flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
+    # (alg_P: the launch is one frequency of an input-side contraction whose reference formulation has P = alg_P)
+    flops = 2 * E * Co * Ci * F * (RADIAL_MID + (alg_P if alg_P is not None else P))
     executed = 2 * E * Co * Ci * F * (Kp + P)
     nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
-    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}',
-                                               executed=executed):
+    tag = f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}' + (f'(in-side of P{alg_P})' if alg_P is not None else '')
+    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=tag, executed=executed):
         _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
 
 

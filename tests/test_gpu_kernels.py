@@ -252,6 +252,44 @@ def test_pairwise_lowrank_matches_fp64(r, P, di, do):
     assert rel_err(out.cpu().numpy(), 2 * ref) < 3e-6
 
 
+@pytest.mark.parametrize('r,di,do', [(15, 0, 3), (15, 1, 3), (31, 1, 2), (15, 0, 1)])
+def test_input_side_contraction_matches_fp64(r, di, do):
+    """Pairs with l_in < l_out on the low-rank path: S = R x (Q FMAs per radial weight), then the basis fold; result vs
+    float64 of the reference order (kernel = R . B first, S:336-343)."""
+    from se3_transformer_pytorch_b200 import ops
+    P, Q = 2 * do + 1, 2 * di + 1
+    if not ops.tc_supported(DEV, 64, P):
+        pytest.skip('tensor-core path needs sm_100')
+    rng = np.random.default_rng(17)
+    Ci, Co = 12, 64
+    pr = _pair_problem(rng, 1, 30, 9, Ci, Co, di, do)
+    E, F = pr['E'], pr['F']
+    Vq, _ = np.linalg.qr(rng.standard_normal((128, r)))
+    Ur = rng.standard_normal((E, r))
+    G = Ur @ Vq.T
+    W3, b3 = pr['W3'].astype(np.float64), pr['b3'].astype(np.float64)
+    R = (G @ W3.T + b3).reshape(E, Co, Ci, F)
+    ref = np.einsum('eoif,eifp->eop', R, pr['T'].reshape(E, Ci, F, P))
+    Kp = 16 * ((r + 1 + 15) // 16)
+    U = np.zeros((E, 64), dtype=np.float32); U[:, :r] = Ur; U[:, r] = 1.0
+    Fp = np.zeros((Co * Ci * F, Kp), dtype=np.float32); Fp[:, :r] = W3 @ Vq; Fp[:, r] = b3
+    X = ops.gather_tiles(cu(pr['x']), cu(pr['idx']))
+    Xd = decode_T(X.cpu().numpy(), (E + 127) // 128, Ci, 1, Q)[:E]   # [E, Ci, Q] == gathered neighbour features
+    xg = pr['x'].reshape(-1, Ci, Q)[pr['idx'].reshape(-1)]
+    assert np.array_equal(Xd, xg)
+    S = torch.empty((F, E, Co, Q), device=DEV)
+    Fv = Fp.reshape(Co, Ci, F, Kp)
+    for f in range(F):
+        img = ops.pack_lowrank(cu(np.ascontiguousarray(Fv[:, :, f, :]).reshape(-1, Kp)), Co, Ci, 1, Kp)
+        ops.pairwise_lr(cu(U), img, X, E, Co, Ci, 1, Q, Kp, S[f], accumulate=False, alg_P=P)
+    out = torch.full((E, Co, P), 5.0, device=DEV)
+    Bp = cu(pr['B']).reshape(-1)
+    ops.fold_basis(S, Bp, E, Co, P, Q, F, out, accumulate=False)
+    assert rel_err(out.cpu().numpy(), ref) < 3e-6
+    ops.fold_basis(S, Bp, E, Co, P, Q, F, out, accumulate=True)
+    assert rel_err(out.cpu().numpy(), 2 * ref) < 3e-6
+
+
 def test_lowrank_basis_of_radial_trunk():
     """Distance-only radial trunks are numerically low rank: a basis of rank <= 31 reproduces the float64 curve to 1e-6 (ops.LOWRANK_TOL),
     and the fp32 kernel outputs at unseen distances stay within fp32 noise of that subspace."""
