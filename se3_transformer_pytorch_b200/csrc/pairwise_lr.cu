@@ -352,6 +352,10 @@ pairwise_lr_kernel(const LrParams prm) {
     mbar_wait(bar_t_full, 0);
     load_t(ta, 0, 0);
     tmem_ld_wait();
+#ifndef SE3_LR_PROBE
+#define SE3_LR_PROBE 0     // measured: early try_wait probes are 0-3 % slower (same-box A/B), kept for experiments
+#endif
+    constexpr bool kProbe = SE3_LR_PROBE && (P >= 5);
     // running ring indices / phase parities of the current step (no div/mod in the loop)
     int st = 0, ts = 0;
     uint32_t ph_acc = 0, ph_t = 0;
@@ -369,9 +373,23 @@ pairwise_lr_kernel(const LrParams prm) {
       load_t(ta, ts, 2);
       contract(rb, tb);
       tmem_ld_wait();
+      int st1 = st + 1, ts1 = ts + 1;
+      uint32_t pa1 = ph_acc, pt1 = ph_t;
+      if (st1 == kLrAcc) { st1 = 0; pa1 ^= 1u; }
+      if (ts1 == kLrTStages) { ts1 = 0; pt1 ^= 1u; }
+      const bool more = s + 1 < NIFB;
       // slot 2
       tmem_ld8(tcol + 96u, rb);
       load_t(tb, ts, 3);
+      // Epilogue-bound pairs (P >= 5): the next step's accumulator and T stage were completed long ago, but an
+      // mbarrier.try_wait still takes ~90-190 cycles to answer; ask now and read the answers after this slot's FMAs.
+      uint32_t ok_acc = 0, ok_t = 0;
+      if constexpr (kProbe) {
+        if (more) {
+          ok_acc = mbar_try_wait(bar_tm_full + 8 * st1, pa1);
+          ok_t = mbar_try_wait(bar_t_full + 8 * ts1, pt1);
+        }
+      }
       contract(ra, ta);
       tmem_ld_wait();
       if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 1);
@@ -380,18 +398,13 @@ pairwise_lr_kernel(const LrParams prm) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
       if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 2);
-      int st1 = st + 1, ts1 = ts + 1;
-      uint32_t pa1 = ph_acc, pt1 = ph_t;
-      if (st1 == kLrAcc) { st1 = 0; pa1 ^= 1u; }
-      if (ts1 == kLrTStages) { ts1 = 0; pt1 ^= 1u; }
       // slot 3, with slot 0 of the next step in flight
-      const bool more = s + 1 < NIFB;
       if (more) {
-        mbar_wait(bar_tm_full + 8 * st1, pa1);
+        if (!ok_acc) mbar_wait(bar_tm_full + 8 * st1, pa1);
         tc_fence_after();
         if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 3);
         tmem_ld8(tcol0 + (uint32_t)(st1 * 128), ra);
-        mbar_wait(bar_t_full + 8 * ts1, pt1);
+        if (!ok_t) mbar_wait(bar_t_full + 8 * ts1, pt1);
         if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 4);
         load_t(ta, ts1, 0);
       }

@@ -8,9 +8,9 @@ B="python bench.py --workload $W --steps 1 --warmup 3 --no-cpu-baseline --profil
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_lr_$W.csv \
     $B > gpurun_out/ncu_launch_run.log 2>&1
 # (3,3) pair of to_k: third launch of the P = 7 instantiation ((2,3) k, (2,3) v, (3,3) k, (3,3) v)
-ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<7' -s 2 -c 1 -o gpurun_out/prof_pairwise_lr_$W \
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.7' -s 2 -c 1 -o gpurun_out/prof_pairwise_lr_$W \
     $B > gpurun_out/ncu_pairwise_run.log 2>&1
 # (0,0) pair of to_k: 5th launch of the P = 1 instantiation (after the 4 conv_in pairs)
-ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<1' -s 4 -c 1 -o gpurun_out/prof_pairwise_lr_p1_$W \
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.1' -s 4 -c 1 -o gpurun_out/prof_pairwise_lr_p1_$W \
     $B > gpurun_out/ncu_pairwise_p1_run.log 2>&1
 ls -la gpurun_out/ | tail -8
