@@ -133,10 +133,14 @@ class CpuSample:
                      f'({self.flops:.3e} sampled vs {forward_flops(wl) / wl["b"]:.3e} per cloud)')
 
     def run(self):
-        t0 = time.perf_counter()
-        self.O.conv_se3(self.feats, self.graph, self.basis, self.P, 'to_v.', self.f_in, self.f_out, pool=False, self_interaction=False,
-                        edge_chunk=self.chunk)
-        return time.perf_counter() - t0
+        # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+        from threadpoolctl import threadpool_limits, threadpool_info
+        with threadpool_limits(limits=os.cpu_count()):
+            self.threads = max([p.get('num_threads', 1) for p in threadpool_info()] or [1])
+            t0 = time.perf_counter()
+            self.O.conv_se3(self.feats, self.graph, self.basis, self.P, 'to_v.', self.f_in, self.f_out, pool=False, self_interaction=False,
+                            edge_chunk=self.chunk)
+            return time.perf_counter() - t0
 
     def clouds_per_s(self, seconds):
         return (self.flops / seconds) / (forward_flops(self.wl) / self.wl['b'])
@@ -159,7 +163,7 @@ def run_reference(args, wl, rank, world):
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, **{k: v for k, v in wl['ctor'].items()}, 'batch_per_gpu': wl['b'], 'n_points': wl['n']},
-        'cpu_baseline': {'value': value, 'unit': 'clouds/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': desc},
+        'cpu_baseline': {'value': value, 'unit': 'clouds/s', 'cores': sample.threads, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': 'clouds/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -369,10 +373,10 @@ def run_ours(args, wl, rank, local_rank, world):
             hbm_kernels[name] = {'achieved_GBs': ach, 'frac_of_hbm_peak': ach / peaks['hbm_gbs'], 'ms_per_step': d['ms'] / args.steps,
                                  'launches_per_step': d['launches'] / args.steps}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only (the reference arm covers every N)
         sample = CpuSample(wl, target_flops=args.cpu_flops)
         dt = sample.run()
-        cpu = {'value': sample.clouds_per_s(dt), 'unit': 'clouds/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample.desc,
+        cpu = {'value': sample.clouds_per_s(dt), 'unit': 'clouds/s', 'cores': sample.threads, 'kind': 'port', 'sample': sample.desc,
                'sample_seconds': dt}
     line = {
         'metric': 'point-clouds/sec fwd', 'value': value, 'unit': 'clouds/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
