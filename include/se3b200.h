@@ -112,12 +112,27 @@ int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, void* image
 int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                         int Kp, int accumulate, float* out, void* stream);
 
+/* As se3_pairwise_lr_fwd, but component p of the kernel is written to out[e*edge_stride + o*channel_stride + p_off[p]]
+ * (p_off: HOST array of P ints, P in {1,2,3,5,7}).  Used by the edge-aligned formulation, where one launch
+ * updates the components (+m, -m) of a component-major [E, P_full, Co] buffer (channel_stride = 1). */
+int se3_pairwise_lr_strided_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
+                                int Kp, int accumulate, float* out, int64_t edge_stride, int channel_stride, const int* p_off,
+                                void* stream);
+
 /* Basis fold of the input-side contraction (pairs with 2 l_in + 1 = Q < P = 2 l_out + 1; S:336-343, 251 reassociated):
  *   out[e,o,p] (+)= sum_{f,q} basis_pair[e,p,q,f] * S[f,e,o,q]
  * where S[f] [E,Co,Q] = se3_pairwise_lr_fwd with F := 1, P := Q, T := the gathered neighbour features in tile layout
  * (se3_tbuild_fwd with an identity basis) and the image of frequency f's rows of Fp.  basis_pair: [E,P,Q,F] of these E edges. */
 int se3_fold_basis_fwd(const float* S, const float* basis_pair, int64_t E, int Co, int P, int Q, int F, int accumulate,
                        float* out, void* stream);
+/* Rotation of the edge-aligned outputs back to the global frame: out[e,o,:] = D_lo(e) out'[e,o,:], D [E,P,P],
+ * out' given as one dense buffer per |m|: part0 [E,Co] (m = 0), part_m [E,Co,2] = components (+m, -m); NULL = zero. */
+int se3_rotate_back_fwd(const float* part0, const float* part1, const float* part2, const float* part3, const float* D,
+                        int64_t E, int Co, int lo, float* out, void* stream);
+/* Same fold with S stored component-major, S[f,e,q,o] ([F,E,Q,Co]): the rotation of the edge-aligned outputs back to the
+ * global frame, out[e,o,:] = D_lo(e) out'[e,:,o]  (F = 1, Q = P, basis_pair = D_lo). */
+int se3_fold_basis_cm_fwd(const float* S, const float* basis_pair, int64_t E, int Co, int P, int Q, int F, int accumulate,
+                          float* out, void* stream);
 
 /* Diagnostic for tools/: as se3_pairwise_lr_fwd; CTA 0 writes clock64 stamps of its warp roles to trace[5][64][8] (u64). */
 int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,

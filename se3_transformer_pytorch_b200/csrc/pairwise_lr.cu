@@ -88,6 +88,9 @@ struct LrParams {
   float* out;
   int64_t E;
   int Co, NIFB, n_mt, n_ob, accumulate, nk16, band_m, band_o, mma_warps, spu, NU;
+  int64_t out_es;          // floats between consecutive edges of the output (Co*P for the dense [E,Co,P] layout)
+  int out_os;              // floats between consecutive output channels of an edge (P for the dense layout)
+  int p_off[7];            // position of the kernel's component p inside an output row
   unsigned long long* trace;   // diagnostic: per-role clock64 stamps of CTA 0 ([5 roles][64 steps][8 events]) or nullptr
 };
 
@@ -419,19 +422,33 @@ pairwise_lr_kernel(const LrParams prm) {
     // write out[e, ob*32 + oq*8 + (0..7), 0..P)
     const int64_t e = mt * SE3_TILE_E + el;
     if (active && e < E) {
-      float* dst = out + ((size_t)e * Co + (size_t)ob * SE3_TILE_O + oq * 8) * P;
+      const int ld = prm.out_os;
+      float* dst = out + (size_t)e * prm.out_es + (size_t)(ob * SE3_TILE_O + oq * 8) * ld;
+      // read-modify-write in two phases (all loads of a batch, then all stores): with run-time strides the compiler has to
+      // assume that a store may alias the next load, and a load -> store -> load chain costs one DRAM round trip per value
+      // (measured: +3.7 ms on a 2.5 ms launch)
+      constexpr int AB = (P <= 3) ? 4 : 1;             // channel pairs per batch (register budget)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
+      for (int a0 = 0; a0 < 4; a0 += AB) {
+        float prev[AB][P][2];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          float v0, v1;
-          unpack2(acc[a][p], v0, v1);
-          float* d0 = dst + (2 * a) * P + p;
-          float* d1 = dst + (2 * a + 1) * P + p;
-          if (accumulate) { v0 += *d0; v1 += *d1; }
-          *d0 = v0;
-          *d1 = v1;
-        }
+        for (int a = 0; a < AB; ++a)
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const float* d0 = dst + (2 * (a0 + a)) * ld + prm.p_off[p];
+            prev[a][p][0] = accumulate ? __ldcg(d0) : 0.f;
+            prev[a][p][1] = accumulate ? __ldcg(d0 + ld) : 0.f;
+          }
+#pragma unroll
+        for (int a = 0; a < AB; ++a)
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            float v0, v1;
+            unpack2(acc[a0 + a][p], v0, v1);
+            float* d0 = dst + (2 * (a0 + a)) * ld + prm.p_off[p];
+            d0[0] = v0 + prev[a][p][0];
+            d0[ld] = v1 + prev[a][p][1];
+          }
       }
     }
   }
@@ -502,11 +519,12 @@ extern "C" int se3_pack_lowrank(const float* Fp, int Co, int Ci, int F, int Kp, 
 }
 
 static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P, int Kp,
-                            int accumulate, float* out, unsigned long long* trace, void* stream) {
+                            int accumulate, float* out, int64_t out_es, int out_os, const int* p_off, unsigned long long* trace, void* stream) {
   using namespace se3;
   SE3_REQUIRE(E > 0 && Co > 0 && Ci > 0 && F > 0, "se3_pairwise_lr_fwd: bad sizes");
   SE3_REQUIRE(Co % SE3_TILE_O == 0, "se3_pairwise_lr_fwd: Co=%d must be a multiple of %d", Co, SE3_TILE_O);
-  SE3_REQUIRE(P == 1 || P == 3 || P == 5 || P == 7, "se3_pairwise_lr_fwd: P=%d unsupported (degree_out <= 3)", P);
+  SE3_REQUIRE(P == 1 || P == 2 || P == 3 || P == 5 || P == 7, "se3_pairwise_lr_fwd: P=%d unsupported (1, 2, 3, 5, 7)", P);
+  SE3_REQUIRE(out_es > 0 && out_os > 0, "se3_pairwise_lr_fwd: bad output strides");
   SE3_REQUIRE(Kp >= 16 && Kp <= 64 && Kp % 16 == 0, "se3_pairwise_lr_fwd: Kp=%d must be 16, 32, 48 or 64", Kp);
   SE3_REQUIRE((ceil_div(E, SE3_TILE_E) + 4) * (Co / SE3_TILE_O) < 2147483647ll, "se3_pairwise_lr_fwd: grid too large");
   LrParams prm;
@@ -521,6 +539,11 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
   prm.n_ob = Co / SE3_TILE_O;
   prm.accumulate = accumulate;
   prm.nk16 = Kp / 16;
+  prm.out_es = out_es;
+  prm.out_os = out_os;
+  for (int p = 0; p < 7; ++p) prm.p_off[p] = (p < P) ? (p_off ? p_off[p] : p) : 0;
+  for (int p = 0; p < P; ++p)
+    SE3_REQUIRE(prm.p_off[p] >= 0 && prm.p_off[p] < out_es, "se3_pairwise_lr_fwd: p_off[%d]=%d outside the edge row", p, prm.p_off[p]);
   prm.spu = lr_steps_per_unit(Kp);
   prm.NU = (int)ceil_div((int64_t)prm.NIFB, (int64_t)prm.spu);
   prm.trace = trace;
@@ -532,6 +555,7 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
 #define SE3_LR_CASE(PP) (trace != nullptr ? launch_lr<PP, 2, true>(prm, s) : csz == 1 ? launch_lr<PP, 1, false>(prm, s) : launch_lr<PP, 2, false>(prm, s))
   switch (P) {
     case 1: return SE3_LR_CASE(1);
+    case 2: return SE3_LR_CASE(2);
     case 3: return SE3_LR_CASE(3);
     case 5: return SE3_LR_CASE(5);
     default: return SE3_LR_CASE(7);
@@ -541,11 +565,20 @@ static int pairwise_lr_impl(const float* U, const void* w_img, const float* T, i
 
 extern "C" int se3_pairwise_lr_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                                    int Kp, int accumulate, float* out, void* stream) {
-  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, nullptr, stream);
+  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, (int64_t)Co * P, P, nullptr, nullptr, stream);
+}
+
+// As se3_pairwise_lr_fwd, writing component p of the kernel to out[e*edge_stride + o*channel_stride + p_off[p]] (p_off: HOST
+// array of P ints): the edge-aligned formulation updates two components (+m, -m) of a component-major
+// [E, P_full, Co] buffer per launch (channel_stride 1: every thread writes 8 consecutive floats per component).
+extern "C" int se3_pairwise_lr_strided_fwd(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F,
+                                           int P, int Kp, int accumulate, float* out, int64_t edge_stride, int channel_stride,
+                                           const int* p_off, void* stream) {
+  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, edge_stride, channel_stride, p_off, nullptr, stream);
 }
 
 // Diagnostic (tools/ only): same launch, and CTA 0 records clock64 stamps of its warp roles into trace[5][64][8].
 extern "C" int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                                      int Kp, int accumulate, float* out, unsigned long long* trace, void* stream) {
-  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, trace, stream);
+  return pairwise_lr_impl(U, w_img, T, E, Co, Ci, F, P, Kp, accumulate, out, (int64_t)Co * P, P, nullptr, trace, stream);
 }

@@ -82,13 +82,12 @@ tbuild_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
 // coalesced 16-byte store per quad.
 constexpr int kTbLanes = 4;     // channel lanes per edge (512 threads per CTA)
 
-template <int P, int Q>
+template <int P, int Q, int F>
 __global__ void __launch_bounds__(kTE * kTbLanes, 1)
 tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ basis,
-                  int64_t E, int64_t mt_begin, int n, int k, int Ci, int F_rt, int ci_per_cta, float* __restrict__ T) {
+                  int64_t E, int64_t mt_begin, int n, int k, int Ci, int ci_per_cta, float* __restrict__ T) {
   constexpr int PH = (P + 3) / 4;
-  constexpr int F = (P < Q) ? P : Q;                     // 2*min(li,lo)+1
-  constexpr int R = P * Q * F;
+  constexpr int R = P * Q * F;                           // F = 2*min(li,lo)+1 for the reference basis; 1 or 2 for caller blocks
   extern __shared__ float Bs[];                          // [R][kTE]
   const int el = threadIdx.x;
   const int lane_c = threadIdx.y;
@@ -142,13 +141,12 @@ tbuild_reg_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, 
   }
 }
 
-template <int P, int Q>
+template <int P, int Q, int F>
 static void launch_reg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* basis, int64_t E, int64_t tb, int n,
-                       int k, int Ci, int F, int cpc, float* T) {
-  constexpr int Fc = (P < Q) ? P : Q;
-  const size_t smem = (size_t)P * Q * Fc * kTE * sizeof(float);
-  cudaFuncSetAttribute(tbuild_reg_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tbuild_reg_kernel<P, Q><<<grid, dim3(kTE, kTbLanes), smem, s>>>(x, idx, basis, E, tb, n, k, Ci, F, cpc, T);
+                       int k, int Ci, int cpc, float* T) {
+  const size_t smem = (size_t)P * Q * F * kTE * sizeof(float);
+  cudaFuncSetAttribute(tbuild_reg_kernel<P, Q, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tbuild_reg_kernel<P, Q, F><<<grid, dim3(kTE, kTbLanes), smem, s>>>(x, idx, basis, E, tb, n, k, Ci, cpc, T);
 }
 
 }  // namespace se3
@@ -168,11 +166,16 @@ extern "C" int se3_tbuild_fwd(const float* x, const int64_t* idx, const float* b
   slabs = (int)ceil_div(Ci, ci_per_cta);
   dim3 grid((unsigned)n_mtiles, (unsigned)slabs);
   cudaStream_t st = as_stream(stream);
-  if (P <= 7 && Q <= 7 && F == std::min(P, Q)) {        // the register variant has F = 2*min(li,lo)+1 compiled in
-#define SE3_TB(PP, QQ) if (P == PP && Q == QQ) launch_reg<PP, QQ>(grid, st, x, idx, basis_pair, E, tile_begin, n, k, Ci, F, ci_per_cta, T);
-    SE3_TB(1, 1) SE3_TB(1, 3) SE3_TB(1, 5) SE3_TB(1, 7) SE3_TB(3, 1) SE3_TB(3, 3) SE3_TB(3, 5) SE3_TB(3, 7)
-    SE3_TB(5, 1) SE3_TB(5, 3) SE3_TB(5, 5) SE3_TB(5, 7) SE3_TB(7, 1) SE3_TB(7, 3) SE3_TB(7, 5) SE3_TB(7, 7)
+  bool done = true;
+#define SE3_TB(PP, QQ, FF) if (P == PP && Q == QQ && F == FF) launch_reg<PP, QQ, FF>(grid, st, x, idx, basis_pair, E, tile_begin, n, k, Ci, ci_per_cta, T); else
+  // reference basis blocks: F = 2*min(li,lo)+1
+  SE3_TB(1, 1, 1) SE3_TB(1, 3, 1) SE3_TB(1, 5, 1) SE3_TB(1, 7, 1) SE3_TB(3, 1, 1) SE3_TB(3, 3, 3) SE3_TB(3, 5, 3) SE3_TB(3, 7, 3)
+  SE3_TB(5, 1, 1) SE3_TB(5, 3, 3) SE3_TB(5, 5, 5) SE3_TB(5, 7, 5) SE3_TB(7, 1, 1) SE3_TB(7, 3, 3) SE3_TB(7, 5, 5) SE3_TB(7, 7, 7)
+  // caller blocks: gathered features (input-side contraction) and the edge-aligned (+m, -m) x (a, b) blocks
+  SE3_TB(3, 3, 1) SE3_TB(2, 3, 2) SE3_TB(2, 5, 2) SE3_TB(2, 7, 2)
+  { done = false; }
 #undef SE3_TB
+  if (done) {
   } else {
     const size_t smem = (size_t)P * Q * kTE * sizeof(float);
     SE3_CUDA_OK(cudaFuncSetAttribute(tbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from . import aligned as _aligned
 
 
 def exists(v):
@@ -278,7 +279,19 @@ class ConvSE3(nn.Module):
                 Fp[:, r] = lin.bias
                 Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
                 Vp[:, :r] = V.float()
-                if input_side(di, do) and pc.num_freq > 1:
+                if use_aligned():
+                    # edge-aligned formulation: images of the weights a_m, b_m = constant combinations of the
+                    # F frequencies (rows (o,i,f) of F'), one image per m
+                    Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp).double()
+                    c0, ca, cb = (t.to(dev) for t in _aligned.aligned_coeffs(di, do))
+                    imgs = [ops.pack_lowrank(torch.einsum('oifk,f->oik', Fv, c0).reshape(-1, Kp).float().contiguous(),
+                                             pc.nc_out, pc.nc_in, 1, Kp)]
+                    for m in range(1, min(di, do) + 1):
+                        ab = torch.stack([torch.einsum('oifk,f->oik', Fv, ca[m - 1]), torch.einsum('oifk,f->oik', Fv, cb[m - 1])], dim=2)
+                        imgs.append(ops.pack_lowrank(ab.reshape(-1, Kp).float().contiguous(), pc.nc_out, pc.nc_in, 2, Kp))
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=None, al_imgs=imgs)
+                    del Fv
+                elif input_side(di, do) and pc.num_freq > 1:
                     # input-side contraction: one image per frequency f (rows (o,i,f) of F'), no combined image
                     Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp)
                     imgs = [ops.pack_lowrank(Fv[:, :, f, :].reshape(-1, Kp).contiguous(), pc.nc_out, pc.nc_in, 1, Kp)
@@ -334,6 +347,23 @@ def input_side(di, do):
     return di < do and di <= 1 and not os.environ.get('SE3B200_NO_INPUT_SIDE')
 
 
+def use_aligned():
+    """Edge-aligned evaluation of the low-rank path: 2 FMAs per radial weight instead of 2 l_out + 1."""
+    return not os.environ.get('SE3B200_NO_ALIGNED')
+
+
+class Geometry:
+    """Per-forward edge geometry shared by every layer; the aligned frames are built on first use."""
+
+    def __init__(self, rel_pos, max_degree):
+        self.rel_pos, self.max_degree, self._frames = rel_pos, max_degree, None
+
+    def frames(self):
+        if self._frames is None:
+            self._frames = _aligned.EdgeFrames(self.rel_pos, self.max_degree)
+        return self._frames
+
+
 def conv_forward(convs, inp, edge_info, rel_dist, basis):
     """Evaluate one or more ConvSE3 that share input features, graph and fibers (to_k / to_v of an attention block)
     in a single sweep: the T blocks (gather x basis) are built once per (degree pair, edge chunk) and consumed by every
@@ -343,7 +373,8 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
     b, n, k = idx.shape
     E = b * n * k
     dev = idx.device
-    flat, plan = basis                       # BasisFlat
+    flat, plan = basis[:2]                   # BasisFlat (+ Geometry)
+    geom = basis[2] if len(basis) > 2 else None
     bpairs = ops.basis_pairs(flat, plan, E)
     n_tiles = (E + ops.TILE_E - 1) // ops.TILE_E
 
@@ -373,7 +404,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 res = (g[pi] - U[pi] @ pp['V'].t()).abs().max() / g[pi].abs().max().clamp(min=1e-30)
                 worst = torch.maximum(worst, res)
                 U[pi, :, pp['r']] = 1.0
-                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'))
+                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'), al_imgs=pp.get('al_imgs'))
             if float(worst) > conv.LR_RUNTIME_TOL:
                 # the fp32 trunk outputs of this forward leave the cached subspace (distances beyond the plan's range)
                 if conv.free_master:
@@ -381,14 +412,50 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                                        'pack_weights(max_distance=...) was given too small a distance')
                 lr = {}                              # evaluate this ConvSE3 with the direct K = 128 kernel
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
-        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr))
+        al = geom is not None and len(lr) == len(conv.pairs) and all(v.get('al_imgs') is not None for v in lr.values())
+        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr, aligned=al))
+    aligned_states = [st for st in states if st['aligned']]
+    states_all, states = states, [st for st in states if not st['aligned']]
 
     # chunk over edge tiles so that the largest T block fits the workspace
     worst = max(ops.t_numel(1, mi, to_order(min(di, do)), to_order(do)) * 4
                 for di, mi in c0.fiber_in for do, _ in c0.fiber_out)
     tiles_per_chunk = max(1, min(n_tiles, T_WORKSPACE_BYTES // worst))
     workspace = None
-    for t0 in range(0, n_tiles, tiles_per_chunk):
+    for t0 in range(0, n_tiles, tiles_per_chunk) if aligned_states else ():
+        # ---- edge-aligned formulation: rotate the neighbour features into the edge frame, two output components per launch
+        tc = min(tiles_per_chunk, n_tiles - t0)
+        e0 = t0 * ops.TILE_E
+        ec = min(E - e0, tc * ops.TILE_E)
+        frames = geom.frames()
+        # out' of degree do lives in one dense buffer per |m|: [edges, C_out] for m = 0, [edges, C_out, 2] = (+m, -m) otherwise
+        # (the kernel's native layout); first contribution overwrites, later input degrees accumulate
+        outp = [{} for _ in aligned_states]
+        for di, mi in c0.fiber_in:
+            for m in range(di + 1):
+                targets = [(do, mo) for do, mo in c0.fiber_out if do >= m]
+                if not targets:
+                    continue
+                Pk = Fk = 1 if m == 0 else 2
+                workspace = ops.tbuild_blocks(inp[str(di)], idx, frames.block(di, m), Pk, Fk, t0, tc, out=workspace)
+                for do, mo in targets:
+                    P = to_order(do)
+                    for st, op in zip(aligned_states, outp):
+                        lrp = st['lr'][(di, do)]
+                        first = (do, m) not in op
+                        if first:
+                            op[(do, m)] = st['outs'][do][e0:e0 + ec] if do == 0 else torch.empty((ec, mo, Pk), dtype=torch.float32, device=dev)
+                        ops.pairwise_lr(lrp['U'][e0:e0 + ec], lrp['al_imgs'][m], workspace, ec, mo, mi, Fk, Pk, lrp['Kp'], op[(do, m)],
+                                        accumulate=not first, alg_units=Fk * 2 * (ops.RADIAL_MID + P))
+        for st, op in zip(aligned_states, outp):
+            for do, mo in c0.fiber_out:
+                if do > 0:                      # back to the global frame: out = D_lo out'
+                    ops.rotate_back([op.get((do, m)) for m in range(do + 1)], frames.D[do][e0:e0 + ec].reshape(-1), ec, mo, do,
+                                    st['outs'][do][e0:e0 + ec])
+                elif (0, 0) not in op:
+                    st['outs'][0][e0:e0 + ec].zero_()
+        del outp
+    for t0 in range(0, n_tiles, tiles_per_chunk) if states else ():
         tc = min(tiles_per_chunk, n_tiles - t0)
         e0 = t0 * ops.TILE_E
         ec = min(E - e0, tc * ops.TILE_E)
@@ -432,7 +499,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 first = False
 
     results = []
-    for st in states:
+    for st in states_all:
         conv = st['conv']
         outputs = {}
         for do, mo in conv.fiber_out:
@@ -783,7 +850,7 @@ class SE3Transformer(nn.Module):
             a = self.adj_emb(adj_indices.gather(2, idx))
             e = torch.cat((e, a), dim=-1) if exists(e) else a
 
-        basis = ops.basis_flat(rel_pos, self.num_degrees - 1)
+        basis = ops.basis_flat(rel_pos, self.num_degrees - 1) + (Geometry(rel_pos, self.num_degrees - 1),)
         edge_info = (idx, nmask, e)
         x = self.conv_in(feats, edge_info, rel_dist=rel_dist, basis=basis)
         for conv, nonlin in self.convs:

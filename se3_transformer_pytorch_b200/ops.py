@@ -35,8 +35,11 @@ _SIGNATURES = {
     'se3_lowrank_image_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
     'se3_pack_lowrank': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_pairwise_lr_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_void_p]),
+    'se3_pairwise_lr_strided_fwd': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'se3_pairwise_lr_trace': (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p, c_void_p, c_void_p]),
     'se3_fold_basis_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_fold_basis_cm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_rotate_back_fwd': (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_void_p, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
@@ -319,13 +322,45 @@ def gather_tiles(x, idx, tile_begin=0, tile_count=None, out=None):
     return out
 
 
-def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate):
-    """out [E,Co,P] (+)= sum_{f,q} basis_pair[e,p,q,f] S[f,e,o,q]; S [F,E,Co,Q], basis_pair the [E,P,Q,F] rows of these edges."""
+def tbuild_blocks(x, idx, blocks, P, F, tile_begin=0, tile_count=None, out=None):
+    """se3_tbuild_fwd with caller-supplied per-edge blocks [E,P,Q,F] (flat): T[e,i,f,p] = sum_q blocks[e,p,q,f] x[b, idx[e], i, q]."""
+    _require_cuda(x, idx, blocks)
+    x = _f32(x)
+    b, n, Ci, Q = x.shape
+    k = idx.shape[-1]
+    E = b * n * k
+    assert blocks.numel() == E * P * Q * F
+    n_tiles = (E + TILE_E - 1) // TILE_E
+    if tile_count is None:
+        tile_count = n_tiles - tile_begin
+    numel = t_numel(tile_count, Ci, F, P)
+    if out is None or out.numel() < numel:
+        out = torch.empty(numel, dtype=torch.float32, device=x.device)
+    nbytes = 4 * (numel + E * P * Q * F + E * Ci * Q) + 8 * E
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * F * P * Q, nbytes=nbytes):
+        _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(blocks), b, n, k, Ci, P, Q, F, tile_begin, tile_count, _p(out), _stream()))
+    return out
+
+
+def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False):
+    """out [E,Co,P] (+)= sum_{f,q} basis_pair[e,p,q,f] S[f,e,o,q]; S [F,E,Co,Q] (or [F,E,Q,Co] if component_major),
+    basis_pair the [E,P,Q,F] rows of these edges."""
     _require_cuda(S, basis_pair, out)
     assert S.is_contiguous() and basis_pair.is_contiguous() and out.is_contiguous()
     nbytes = 4 * (S.numel() + basis_pair.numel() + out.numel() * (2 if accumulate else 1))
     with torch.cuda.device(out.device), _timed('fold_basis', flops=2 * E * Co * P * Q * F, nbytes=nbytes):
-        _check(lib().se3_fold_basis_fwd(_p(S), _p(basis_pair), E, Co, P, Q, F, int(accumulate), _p(out), _stream()))
+        fn = lib().se3_fold_basis_cm_fwd if component_major else lib().se3_fold_basis_fwd
+        _check(fn(_p(S), _p(basis_pair), E, Co, P, Q, F, int(accumulate), _p(out), _stream()))
+
+
+def rotate_back(parts, D, E, Co, lo, out):
+    """out [E,Co,2lo+1] = D_lo(e) out'(e): parts[0] [E,Co] (m = 0), parts[m] [E,Co,2] (components +m, -m) or None."""
+    _require_cuda(D, out)
+    ptrs = [(_p(t) if t is not None else None) for t in (list(parts) + [None] * 4)[:4]]
+    P = 2 * lo + 1
+    nbytes = 4 * (2 * E * Co * P + E * P * P)
+    with torch.cuda.device(out.device), _timed('fold_basis', flops=2 * E * Co * P * P, nbytes=nbytes):
+        _check(lib().se3_rotate_back_fwd(*ptrs, _p(D), E, Co, lo, _p(out), _stream()))
 
 
 def pairwise_simt(g, W3, b3, T, E, Co, Ci, F, P, out, accumulate):
@@ -374,18 +409,26 @@ def pack_lowrank(Fp, Co, Ci, F, Kp):
     return img
 
 
-def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None):
+def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, out_strides=None, p_off=None, alg_units=None):
     """Low-rank radial path: U [E,64] fp32 (G V | 1 | 0), w_img from pack_lowrank."""
     _require_cuda(U, w_img, T, out)
     # algorithmic work of the reference formulation (SURVEY.md 8d): 2*128 (radial GEMM) + 2P (contraction) per R element;
     # executed work: the GEMM has K = Kp instead of 128
     # (alg_P: the launch is one frequency of an input-side contraction whose reference formulation has P = alg_P)
+    # (alg_units: reference-formulation FLOPs per (edge, o, i) that this launch stands for, when it is not F*(2*128 + 2P))
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + (alg_P if alg_P is not None else P))
+    if alg_units is not None:
+        flops = E * Co * Ci * alg_units
     executed = 2 * E * Co * Ci * F * (Kp + P)
     nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
     tag = f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}' + (f'(in-side of P{alg_P})' if alg_P is not None else '')
     with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=tag, executed=executed):
-        _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
+        if out_strides is None:
+            _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
+        else:
+            offs = (ctypes.c_int * P)(*p_off)
+            _check(lib().se3_pairwise_lr_strided_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out),
+                                                     out_strides[0], out_strides[1], offs, _stream()))
 
 
 # max-abs residual of the radial basis relative to max|G|.  The fp32 trunk itself carries ~6e-7..1e-6 of rounding noise

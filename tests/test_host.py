@@ -73,3 +73,34 @@ def test_basis_plan_shapes():
     plan = ops.BasisPlan(3, 'cpu')
     assert len(plan.pairs) == 16 and plan.rows_per_edge == 1092
     assert plan.col.numel() == 1132                                   # non-zeros of the 44 Q_J tables
+
+
+def test_aligned_frames_reproduce_the_reference_basis():
+    """Host math of the edge-aligned formulation, on CPU against the oracle: harmonics, Wigner matrices
+    from rotated sample points, the (a, -b; b, a) structure of the basis on the axis, and the identity
+    B(r) = D_lo B(a) D_li^T including coincident points (r = 0 -> the reference evaluates the basis on the axis)."""
+    import numpy as np
+    import torch
+    from oracle import se3_oracle as O
+    from se3_transformer_pytorch_b200 import aligned as AL
+    torch.manual_seed(0)
+    L = 3
+    d = torch.randn(64, 3, dtype=torch.float64)
+    d[0] = 0.0
+    d[1] = torch.tensor([0.0, -2.0, 0.0])            # opposite to the axis
+    d[2] = torch.tensor([0.0, 3.0, 0.0])
+    unit = d / d.norm(dim=-1, keepdim=True).clamp(min=1e-300)
+    Y = AL.real_sh64(unit[1:], 2 * L)
+    Yo = O.real_spherical_harmonics(unit[1:].numpy(), 2 * L)
+    assert max(float(np.abs(Y[l].numpy() - Yo[l]).max()) for l in range(2 * L + 1)) < 1e-12
+    fr = AL.EdgeFrames(d.reshape(1, 1, -1, 3), L)
+    Bo = O.get_basis(d.numpy(), L)
+    Ba = O.get_basis(np.array([AL.AXIS]), L)
+    for li in range(L + 1):
+        for lo in range(L + 1):
+            c0, ca, cb = AL.aligned_coeffs(li, lo)       # asserts the block structure internally
+            ba = np.asarray(Ba[f'{li},{lo}'])[0]
+            assert np.allclose(c0.numpy(), ba[lo, li, :], atol=1e-7)
+            pred = np.einsum('epr,rsf,eqs->epqf', fr.D[lo].double().numpy(), ba, fr.D[li].double().numpy())
+            ref = np.asarray(Bo[f'{li},{lo}'])
+            assert np.abs(pred - ref).max() < 2e-6 * max(1.0, np.abs(ref).max()), (li, lo)
