@@ -354,10 +354,13 @@ def run_ours(args, wl, rank, local_rank, world):
                     'executed_tflops': d['executed'] / (d['ms'] / 1e3) / 1e12}
             if top == 'pairwise_lr':
                 # the fp32 SIMT pipe is what this kernel saturates: 2P FLOPs per R element on FFMA2
-                roof['note'] = ('achieved = algorithmic FLOPs of the reference formulation (SURVEY 8d: 2*128 + 2*(2lo+1) per R element) / '
-                                'CUDA-event time.  The low-rank radial path executes the GEMM with K = r+1 <= 64 instead of 128 '
-                                '(executed_tflops), in 3 fp16 passes; the kernel is then bound by its fp32 epilogue (2lo+1 FMAs per R '
-                                'element on the FFMA2 pipe) and per-step synchronisation, not by the tensor pipe or HBM')
+                roof['note'] = ('achieved = algorithmic FLOPs of the REFERENCE formulation (SURVEY 8d: 2*128 + 2*(2lo+1) per radial weight) / '
+                                'CUDA-event time, as the contract asks; it can exceed the tensor peak because this path does less work for '
+                                'the same result: the radial GEMM runs with K = r+1 <= 32 instead of 128 (low-rank radial basis) and the '
+                                'edge-aligned frame needs 2 instead of 2lo+1 fp32 FMAs per radial weight.  executed_tflops counts what is '
+                                'issued (3 fp16 MMA passes of K = Kp + the fp32 FMAs); executed_frac = executed_tflops / peak.  The kernel is '
+                                'bound by MMA issue + per-step synchronisation (tensor pipe ~55 % active), not by HBM')
+                roof['executed_frac'] = roof['executed_tflops'] / peaks['bf16_sustained']
             else:
                 roof['note'] = ('achieved = algorithmic FLOPs (2*128 + 2*(2lo+1) per R element); the kernel issues 3 fp16 MMA passes '
                                 'per algorithmic GEMM FLOP for fp32 parity, so tensor-pipe work is ~3x this figure')

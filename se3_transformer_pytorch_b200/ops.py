@@ -419,7 +419,7 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, o
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + (alg_P if alg_P is not None else P))
     if alg_units is not None:
         flops = E * Co * Ci * alg_units
-    executed = 2 * E * Co * Ci * F * (Kp + P)
+    executed = 2 * E * Co * Ci * F * (3 * Kp + P)          # issued: 3 fp16 MMA passes of K = Kp + P fp32 FMAs per R element
     nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
     tag = f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}' + (f'(in-side of P{alg_P})' if alg_P is not None else '')
     with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=tag, executed=executed):

@@ -7,10 +7,10 @@ W=${1:-cfg2_depth1}
 B="python bench.py --workload $W --steps 1 --warmup 3 --no-cpu-baseline --profile-range"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_lr_$W.csv \
     $B > gpurun_out/ncu_launch_run.log 2>&1
-# (3,3) pair of to_k: third launch of the P = 7 instantiation ((2,3) k, (2,3) v, (3,3) k, (3,3) v)
-ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.7' -s 2 -c 1 -o gpurun_out/prof_pairwise_lr_$W \
+# edge-aligned path: a (+m,-m) x (a,b) launch (P = 2, F = 2) of the attention block (the 11th of that instantiation)
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.2' -s 10 -c 1 -o gpurun_out/prof_pairwise_lr_$W \
     $B > gpurun_out/ncu_pairwise_run.log 2>&1
-# (0,0) pair of to_k: 5th launch of the P = 1 instantiation (after the 4 conv_in pairs)
-ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.1' -s 4 -c 1 -o gpurun_out/prof_pairwise_lr_p1_$W \
+# an m = 0 launch (P = 1, F = 1) of the attention block that accumulates (13th of that instantiation)
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pairwise_lr_kernel<.int.1' -s 12 -c 1 -o gpurun_out/prof_pairwise_lr_p1_$W \
     $B > gpurun_out/ncu_pairwise_p1_run.log 2>&1
 ls -la gpurun_out/ | tail -8
