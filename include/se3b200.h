@@ -12,6 +12,8 @@
  *                                                                                               se3_pairwise_{simt,tc}_fwd
  *   masked_mean pooling of ConvSE3                     utils.py:72-80, S:256-257             -> se3_pool_fwd
  *   AttentionSE3.forward logits/softmax/aggregate      se3_transformer_pytorch.py:476-517    -> se3_attn_fwd
+ *     (low-rank radial path: se3_pack_lowrank + se3_pairwise_lr_fwd / _strided_fwd, se3_fold_basis_fwd, se3_rotate_back_fwd:
+ *      the same product re-associated)
  *   NormSE3.forward (next to the hot path)  se3_transformer_pytorch.py:130-152    -> se3_norm_fwd
  *
  * Conventions

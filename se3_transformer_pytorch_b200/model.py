@@ -394,17 +394,27 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
             else:
                 plan = conv.lowrank_plan(float(rel_dist.max()))      # cached; one host sync for the distance range
         if plan is not None and plan['pairs']:
-            U = torch.zeros((len(conv.pairs), E, 64), dtype=torch.float32, device=dev)
-            worst = torch.zeros((), dtype=torch.float32, device=dev)
+            # U = G V for every pair in one batched GEMM, the residual check of the cached subspace in a second one
+            if 'Vstack' not in plan:
+                Vs = torch.zeros((len(conv.pairs), ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
+                ones_col = torch.zeros(len(conv.pairs), dtype=torch.long, device=dev)
+                have = torch.zeros(len(conv.pairs), dtype=torch.bool, device=dev)
+                for pi, pair in enumerate(conv.pairs):
+                    pp = plan['pairs'].get(pair)
+                    if pp is not None:
+                        Vs[pi] = pp['V']
+                        ones_col[pi] = pp['r']
+                        have[pi] = True
+                plan['Vstack'], plan['ones_col'], plan['have'] = Vs, ones_col, have
+            Vs = plan['Vstack']
+            U = torch.bmm(g, Vs)                                           # [pairs, E, 64]
+            resid = (g - torch.bmm(U, Vs.transpose(1, 2))).abs().amax(dim=(1, 2)) / g.abs().amax(dim=(1, 2)).clamp(min=1e-30)
+            worst = torch.where(plan['have'], resid, torch.zeros_like(resid)).max()
+            U[torch.arange(len(conv.pairs), device=dev), :, plan['ones_col']] = 1.0
             for pi, pair in enumerate(conv.pairs):
                 pp = plan['pairs'].get(pair)
-                if pp is None:
-                    continue
-                torch.matmul(g[pi], pp['V'], out=U[pi])
-                res = (g[pi] - U[pi] @ pp['V'].t()).abs().max() / g[pi].abs().max().clamp(min=1e-30)
-                worst = torch.maximum(worst, res)
-                U[pi, :, pp['r']] = 1.0
-                lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'), al_imgs=pp.get('al_imgs'))
+                if pp is not None:
+                    lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'), al_imgs=pp.get('al_imgs'))
             if float(worst) > conv.LR_RUNTIME_TOL:
                 # the fp32 trunk outputs of this forward leave the cached subspace (distances beyond the plan's range)
                 if conv.free_master:
