@@ -39,6 +39,13 @@ constexpr uint32_t kLrUnitBytes = 2 * kSubBytes;   // one W tile: [hi 16 KiB | l
 #ifndef SE3_LR_DBG_TDIV
 #define SE3_LR_DBG_TDIV 1
 #endif
+// 1: one "step" barrier pair (accumulator tile + T stage) instead of separate accumulator / T barriers: the epilogue pays one
+// mbarrier wait and one arrive per step.  step_full[s % R] <- tcgen05.commit of the step's MMAs + complete_tx of its T stage
+// (count 2 + tx bytes); step_empty[s % R] <- the 16 epilogue warps; the MMA warps reuse the TMEM buffer of step s-3 after
+// step_empty of that step, the T producer a stage after step_empty of step s-R.
+#ifndef SE3_LR_MERGED
+#define SE3_LR_MERGED 0
+#endif
 constexpr int kLrWSlots = SE3_LR_W_SLOTS;
 constexpr int kLrTStages = SE3_LR_T_STAGES;
 constexpr int kLrAcc = 3;                          // TMEM accumulator buffers (the MMA -> epilogue -> MMA round trip is long)
@@ -157,7 +164,7 @@ pairwise_lr_kernel(const LrParams prm) {
       mbar_init(bar_w_empty + 8 * s, CSZ * spu);   // every step of the unit commits once per CTA of the cluster
     }
     for (int s = 0; s < kLrTStages; ++s) {
-      mbar_init(bar_t_full + 8 * s, 1);
+      mbar_init(bar_t_full + 8 * s, SE3_LR_MERGED ? 2 : 1);
       mbar_init(bar_t_empty + 8 * s, 16);
     }
     for (int s = 0; s < kLrAcc; ++s) {
@@ -232,7 +239,14 @@ pairwise_lr_kernel(const LrParams prm) {
         const int slot = un % kLrWSlots;
         const uint32_t wph = (uint32_t)(un / kLrWSlots) & 1u;
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 0);
+#if SE3_LR_MERGED
+        if (s >= kLrAcc) {                      // the accumulator buffer was last used by step s - kLrAcc
+          const int sp = s - kLrAcc;
+          mbar_wait(bar_t_empty + 8 * (sp % kLrTStages), (uint32_t)(sp / kLrTStages) & 1u);
+        }
+#else
         mbar_wait(bar_tm_empty + 8 * st, ph ^ 1u);
+#endif
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 1);
         mbar_wait(bar_w_full + 8 * slot, wph);
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 2);
@@ -258,7 +272,11 @@ pairwise_lr_kernel(const LrParams prm) {
           }
           if (CSZ == 1) tc_commit(bar_w_empty + 8 * slot);
           else tc_commit_mc(bar_w_empty + 8 * slot, kMask);
+#if SE3_LR_MERGED
+          tc_commit(bar_t_full + 8 * (s % kLrTStages));
+#else
           tc_commit(bar_tm_full + 8 * st);
+#endif
         }
         __syncwarp();
         if constexpr (TRACE) lr_stamp(prm.trace, 0, s, 4);
@@ -349,10 +367,16 @@ pairwise_lr_kernel(const LrParams prm) {
     };
     uint32_t ra[8], rb[8];
     float4 ta[PH], tb[PH];
+#if SE3_LR_MERGED
+    mbar_wait(bar_t_full, 0);
+    tc_fence_after();
+    tmem_ld8(tcol0, ra);
+#else
     mbar_wait(bar_tm_full, 0);
     tc_fence_after();
     tmem_ld8(tcol0, ra);
     mbar_wait(bar_t_full, 0);
+#endif
     load_t(ta, 0, 0);
     tmem_ld_wait();
 #ifndef SE3_LR_PROBE
@@ -399,22 +423,35 @@ pairwise_lr_kernel(const LrParams prm) {
       // every accumulator column of this step is in registers: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
+#if SE3_LR_MERGED
+      // (the LDS of the last slot have been issued and the arrive is a release: the T stage goes back with the accumulator)
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
+#else
       if (lane == 0) mbar_arrive(bar_tm_empty + 8 * st);
+#endif
       if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 2);
       // slot 3, with slot 0 of the next step in flight
       if (more) {
+#if SE3_LR_MERGED
+        mbar_wait(bar_t_full + 8 * ts1, pt1);
+#else
         if (!ok_acc) mbar_wait(bar_tm_full + 8 * st1, pa1);
+#endif
         tc_fence_after();
         if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 3);
         tmem_ld8(tcol0 + (uint32_t)(st1 * 128), ra);
+#if !SE3_LR_MERGED
         if (!ok_t) mbar_wait(bar_t_full + 8 * ts1, pt1);
+#endif
         if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 4);
         load_t(ta, ts1, 0);
       }
       contract(rb, tb);
       if (more) tmem_ld_wait();
       __syncwarp();
+#if !SE3_LR_MERGED
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * ts);
+#endif
       if constexpr (TRACE) if (trole > 0) lr_stamp(prm.trace, trole, s, 5);
       st = st1; ts = ts1; ph_acc = pa1; ph_t = pt1;
     }
