@@ -262,24 +262,26 @@ class ConvSE3(nn.Module):
             grid = torch.linspace(0.0, D, self.LR_GRID, device=dev, dtype=torch.float64).unsqueeze(-1)
             feat = self.encode_dist(grid)
             pairs = {}
+            bases = {}
             for di, do in self.pairs:
-                if not self.tc_eligible(di, do):
-                    continue
+                pc = self.kernel_unary[f'({di},{do})']
+                if self.tc_eligible(di, do) and pc.rp.net['6'].weight.numel() > 0:
+                    basis = ops.lowrank_basis(pc.rp.trunk64(feat))
+                    if basis is not None:
+                        bases[(di, do)] = basis
+            # the edge-aligned images serve a ConvSE3 only if EVERY pair has a plan (all launches of an output degree then
+            # accumulate in the aligned frame); otherwise keep the global-frame images of 4.2-4.3 for the covered pairs
+            aligned_images = use_aligned() and len(bases) == len(self.pairs)
+            for (di, do), (r, V) in bases.items():
                 pc = self.kernel_unary[f'({di},{do})']
                 lin = pc.rp.net['6']
-                if lin.weight.numel() == 0:
-                    continue
-                basis = ops.lowrank_basis(pc.rp.trunk64(feat))
-                if basis is None:
-                    continue
-                r, V = basis
                 Kp = 16 * ((r + 1 + 15) // 16)
                 Fp = torch.zeros((lin.weight.shape[0], Kp), dtype=torch.float32, device=dev)
                 Fp[:, :r] = (lin.weight.double() @ V).float()
                 Fp[:, r] = lin.bias
                 Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
                 Vp[:, :r] = V.float()
-                if use_aligned():
+                if aligned_images:
                     # edge-aligned formulation: images of the weights a_m, b_m = constant combinations of the
                     # F frequencies (rows (o,i,f) of F'), one image per m
                     Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp).double()
@@ -423,6 +425,12 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 lr = {}                              # evaluate this ConvSE3 with the direct K = 128 kernel
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
         al = geom is not None and len(lr) == len(conv.pairs) and all(v.get('al_imgs') is not None for v in lr.values())
+        if not al and any(v.get('img') is None and v.get('imgs_f') is None for v in lr.values()):
+            # the plan holds edge-aligned images only; they need the per-forward Geometry
+            if geom is None:
+                raise RuntimeError('ConvSE3 was called with a (flat, plan) basis: the edge-aligned low-rank plan needs the third element, '
+                                   'model.Geometry(rel_pos, max_degree), as SE3Transformer.forward passes it (or set SE3B200_NO_ALIGNED=1)')
+            lr = {}                                  # mixed eligibility inside one ConvSE3: direct kernels for this forward
         states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr, aligned=al))
     aligned_states = [st for st in states if st['aligned']]
     states_all, states = states, [st for st in states if not st['aligned']]
