@@ -104,3 +104,37 @@ def test_aligned_frames_reproduce_the_reference_basis():
             pred = np.einsum('epr,rsf,eqs->epqf', fr.D[lo].double().numpy(), ba, fr.D[li].double().numpy())
             ref = np.asarray(Bo[f'{li},{lo}'])
             assert np.abs(pred - ref).max() < 2e-6 * max(1.0, np.abs(ref).max()), (li, lo)
+
+
+def test_lowrank_plan_image_selection(monkeypatch):
+    """Host logic of ConvSE3.lowrank_plan on CPU (the CUDA packer is stubbed): distance-only radial trunks factor with rank
+    <= 31, every pair of an all-eligible ConvSE3 gets edge-aligned images (one per |m|, F = 1 or 2 weight columns), a
+    ConvSE3 with an ineligible pair keeps the global-frame images for the pairs it does cover."""
+    import torch
+    from se3_transformer_pytorch_b200 import ops, model as M
+    calls = []
+
+    def fake_pack(Fp, Co, Ci, F, Kp):
+        assert Fp.shape == (Co * Ci * F, Kp) and Fp.dtype == torch.float32 and Fp.is_contiguous()
+        calls.append((Co, Ci, F, Kp))
+        return torch.zeros(1)
+
+    monkeypatch.setattr(ops, 'pack_lowrank', fake_pack)
+    monkeypatch.delenv('SE3B200_NO_ALIGNED', raising=False)
+    torch.manual_seed(0)
+    fin, fout = M.Fiber([(0, 32), (1, 32), (2, 32)]), M.Fiber([(0, 32), (1, 32), (2, 32)])
+    monkeypatch.setattr(M.ConvSE3, 'tc_eligible', lambda self, di, do: True)
+    conv = M.ConvSE3(fin, fout, edge_dim=0, pool=False, self_interaction=False)
+    plan = conv.lowrank_plan(4.0)
+    assert set(plan['pairs']) == set(conv.pairs)
+    for (di, do), pp in plan['pairs'].items():
+        assert pp['r'] <= 31 and pp['Kp'] in (16, 32)
+        assert pp['img'] is None and pp['imgs_f'] is None and len(pp['al_imgs']) == 1 + min(di, do)
+    assert sorted(c[2] for c in calls) == [1] * 9 + [2] * 5          # 9 pairs: one m = 0 image each; sum of min(di,do) = 5
+    calls.clear()
+    monkeypatch.setattr(M.ConvSE3, 'tc_eligible', lambda self, di, do: (di, do) != (2, 2))
+    conv2 = M.ConvSE3(fin, fout, edge_dim=0, pool=False, self_interaction=False)
+    plan2 = conv2.lowrank_plan(4.0)
+    assert (2, 2) not in plan2['pairs'] and len(plan2['pairs']) == 8
+    assert all(pp.get('al_imgs') is None and (pp['img'] is not None or pp['imgs_f'] is not None) for pp in plan2['pairs'].values())
+    assert conv2.lowrank_plan(3.0) is plan2                          # cached while the distance range is covered
