@@ -343,13 +343,15 @@ def run_ours(args, wl, rank, local_rank, world):
         d = kern[top]
         if top.startswith('pairwise'):
             ach = d['flops'] / (d['ms'] / 1e3) / 1e12
-            traffic = None
+            traffic, traffic_detail = None, None
             tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
             if os.path.exists(tpath):
                 with open(tpath) as f:
-                    traffic = json.load(f).get(top)
+                    traffic_detail = json.load(f).get(top)
+                if isinstance(traffic_detail, dict):
+                    traffic = traffic_detail.get('dram_bytes_per_launch')      # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['bf16_sustained'], 'traffic': traffic, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
+                    'frac': ach / peaks['bf16_sustained'], 'traffic': traffic, 'traffic_detail': traffic_detail, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
                     'avg_launch_ms': d['ms'] / d['launches'], 'share_of_step': d['ms'] / ms_res,
                     'executed_tflops': d['executed'] / (d['ms'] / 1e3) / 1e12}
             if top == 'pairwise_lr':
