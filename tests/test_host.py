@@ -138,3 +138,91 @@ def test_lowrank_plan_image_selection(monkeypatch):
     assert (2, 2) not in plan2['pairs'] and len(plan2['pairs']) == 8
     assert all(pp.get('al_imgs') is None and (pp['img'] is not None or pp['imgs_f'] is not None) for pp in plan2['pairs'].values())
     assert conv2.lowrank_plan(3.0) is plan2                          # cached while the distance range is covered
+
+
+def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
+    """conv_forward's edge-aligned dispatch (plan images, per-(l_in, m) tiles, (+m,-m) buffers, rotate-back, edge chunking)
+    with every CUDA op replaced by a float64 torch emulation of its contract, against the reference order of operations
+    (kernel = R . B first, S:336-343, with the oracle's basis).  Host logic only: the CUDA kernels have their own GPU tests."""
+    import numpy as np
+    import torch
+    from oracle import se3_oracle as O
+    from se3_transformer_pytorch_b200 import ops, model as M
+
+    torch.manual_seed(0)
+    b, n, k, C = 1, 40, 8, 32
+    L = 2
+    fin, fout = M.Fiber([(d, C) for d in range(L + 1)]), M.Fiber([(d, C) for d in range(L + 1)])
+    monkeypatch.delenv('SE3B200_NO_ALIGNED', raising=False)
+    monkeypatch.setattr(M.ConvSE3, 'tc_eligible', lambda self, di, do: True)
+    monkeypatch.setattr(ops, 'lowrank_enabled', lambda E: True)
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
+    monkeypatch.setattr(M, 'T_WORKSPACE_BYTES', ops.t_numel(1, C, 2, 2) * 4)       # one edge tile per chunk -> 3 chunks
+    monkeypatch.setattr(ops, 'pack_lowrank', lambda Fp, Co, Ci, F, Kp: Fp.double().clone())  # "image" = F' itself
+
+    conv = M.ConvSE3(fin, fout, edge_dim=0, pool=False, self_interaction=False)
+
+    def radial_trunk(feat, params, num_pairs):
+        return torch.stack([conv.kernel_unary[f'({di},{do})'].rp.trunk64(feat.double()) for di, do in conv.pairs]).float()
+
+    def tbuild_blocks(x, idx, blocks, P, F, tile_begin=0, tile_count=None, out=None):
+        bb, nn, Ci, Q = x.shape
+        E = idx.numel()
+        e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
+        xj = x.reshape(bb * nn, Ci, Q)[(idx + torch.arange(bb).view(-1, 1, 1) * nn).reshape(-1)][e0:e1].double()
+        blk = blocks.reshape(E, P, Q, F)[e0:e1].double()
+        return torch.einsum('epqf,eiq->eifp', blk, xj)                             # T[e,i,f,p]
+
+    def pairwise_lr(U, img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, out_strides=None, p_off=None, alg_units=None):
+        assert out_strides is None and T.shape == (E, Ci, F, P) and out.shape[0] == E
+        R = (U[:, :Kp].double() @ img.t()).reshape(E, Co, Ci, F)                    # bias rides on the ones column of U
+        res = torch.einsum('eoif,eifp->eop', R, T).reshape(out.shape)
+        out.copy_((out.double() + res if accumulate else res).float())
+
+    def rotate_back(parts, D, E, Co, lo, out):
+        P = 2 * lo + 1
+        v = torch.zeros((E, Co, P), dtype=torch.float64)
+        if parts[0] is not None:
+            v[:, :, lo] = parts[0].reshape(E, Co).double()
+        for m in range(1, lo + 1):
+            if parts[m] is not None:
+                v[:, :, lo + m], v[:, :, lo - m] = parts[m][:, :, 0].double(), parts[m][:, :, 1].double()
+        out.copy_(torch.einsum('epn,eon->eop', D.reshape(E, P, P).double(), v).float())
+
+    for name, fn in (('radial_trunk', radial_trunk), ('tbuild_blocks', tbuild_blocks), ('pairwise_lr', pairwise_lr),
+                     ('rotate_back', rotate_back)):
+        monkeypatch.setattr(ops, name, fn)
+
+    coors = torch.randn(b, n, 3)
+    idx = torch.stack([torch.randperm(n - 1)[:k] for _ in range(b * n)]).reshape(b, n, k)
+    idx = idx + (idx >= torch.arange(n).view(1, n, 1)).long()                        # neighbours != self
+    rel_pos = coors[0][:, None, :] - coors[0][idx[0]]                                # x_i - x_j   (S:1222)
+    rel_pos = rel_pos.reshape(b, n, k, 3)
+    rel_dist = rel_pos.norm(dim=-1)
+    inp = {str(d): torch.randn(b, n, C, 2 * d + 1) for d in range(L + 1)}
+
+    class FakePlan:
+        pairs, pair_base, pair_rows = [], [], []
+
+    basis = (torch.zeros(0), FakePlan(), M.Geometry(rel_pos, L))
+    nmask = torch.ones(b, n, k, dtype=torch.bool)
+    with torch.no_grad():
+        out = M.conv_forward([conv], inp, (idx, nmask, None), rel_dist, basis)[0]
+
+    # reference order of operations in float64
+    E = b * n * k
+    Bo = O.get_basis(rel_pos.reshape(E, 3).double().numpy(), L)
+    feat = rel_dist.reshape(E, 1).double()
+    worst = 0.0
+    for do in range(L + 1):
+        ref = np.zeros((E, C, 2 * do + 1))
+        for di in range(L + 1):
+            pc = conv.kernel_unary[f'({di},{do})']
+            lin = pc.rp.net['6']
+            g = pc.rp.trunk64(feat)
+            R = (g @ lin.weight.double().t() + lin.bias.double()).reshape(E, C, C, pc.num_freq).detach().numpy()
+            xj = inp[str(di)].reshape(n, C, 2 * di + 1)[idx.reshape(-1)].double().numpy()
+            ref += np.einsum('eoif,epqf,eiq->eop', R, np.asarray(Bo[f'{di},{do}']), xj)
+        got = out[str(do)].reshape(E, C, 2 * do + 1).numpy()
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+    assert worst < 2e-5, worst
