@@ -140,8 +140,10 @@ def test_lowrank_plan_image_selection(monkeypatch):
     assert conv2.lowrank_plan(3.0) is plan2                          # cached while the distance range is covered
 
 
-def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
-    """conv_forward's edge-aligned dispatch (plan images, per-(l_in, m) tiles, (+m,-m) buffers, rotate-back, edge chunking)
+@pytest.mark.parametrize('frame', ['aligned', 'global'])
+def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
+    """conv_forward's low-rank dispatch -- edge-aligned and global frame with input-side contraction
+    (4.2-4.3) (plan images, per-(l_in, m) tiles, (+m,-m) buffers, rotate-back, edge chunking)
     with every CUDA op replaced by a float64 torch emulation of its contract, against the reference order of operations
     (kernel = R . B first, S:336-343, with the oracle's basis).  Host logic only: the CUDA kernels have their own GPU tests."""
     import numpy as np
@@ -153,7 +155,10 @@ def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
     b, n, k, C = 1, 40, 8, 32
     L = 2
     fin, fout = M.Fiber([(d, C) for d in range(L + 1)]), M.Fiber([(d, C) for d in range(L + 1)])
-    monkeypatch.delenv('SE3B200_NO_ALIGNED', raising=False)
+    if frame == 'aligned':
+        monkeypatch.delenv('SE3B200_NO_ALIGNED', raising=False)
+    else:
+        monkeypatch.setenv('SE3B200_NO_ALIGNED', '1')
     monkeypatch.setattr(M.ConvSE3, 'tc_eligible', lambda self, di, do: True)
     monkeypatch.setattr(ops, 'lowrank_enabled', lambda E: True)
     monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
@@ -173,6 +178,25 @@ def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
         blk = blocks.reshape(E, P, Q, F)[e0:e1].double()
         return torch.einsum('epqf,eiq->eifp', blk, xj)                             # T[e,i,f,p]
 
+    def gather_rows(x, idx, e0, e1):
+        bb, nn, Ci, Q = x.shape
+        return x.reshape(bb * nn, Ci, Q)[(idx + torch.arange(bb).view(-1, 1, 1) * nn).reshape(-1)][e0:e1].double()
+
+    def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=None):
+        E = idx.numel()
+        P, Q, F = 2 * d_out + 1, 2 * d_in + 1, 2 * min(d_in, d_out) + 1
+        e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
+        return torch.einsum('epqf,eiq->eifp', basis_pair.reshape(E, P, Q, F)[e0:e1].double(), gather_rows(x, idx, e0, e1))
+
+    def gather_tiles(x, idx, tile_begin=0, tile_count=None, out=None):
+        E = idx.numel()
+        e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
+        return gather_rows(x, idx, e0, e1).unsqueeze(2)                             # [e, i, f = 1, q]
+
+    def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False):
+        res = torch.einsum('epqf,feoq->eop', basis_pair.reshape(E, P, Q, F).double(), S.double())
+        out.copy_((out.double() + res if accumulate else res).float())
+
     def pairwise_lr(U, img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, out_strides=None, p_off=None, alg_units=None):
         assert out_strides is None and T.shape == (E, Ci, F, P) and out.shape[0] == E
         R = (U[:, :Kp].double() @ img.t()).reshape(E, Co, Ci, F)                    # bias rides on the ones column of U
@@ -190,7 +214,7 @@ def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
         out.copy_(torch.einsum('epn,eon->eop', D.reshape(E, P, P).double(), v).float())
 
     for name, fn in (('radial_trunk', radial_trunk), ('tbuild_blocks', tbuild_blocks), ('pairwise_lr', pairwise_lr),
-                     ('rotate_back', rotate_back)):
+                     ('rotate_back', rotate_back), ('tbuild', tbuild), ('gather_tiles', gather_tiles), ('fold_basis', fold_basis)):
         monkeypatch.setattr(ops, name, fn)
 
     coors = torch.randn(b, n, 3)
@@ -201,17 +225,16 @@ def test_aligned_conv_dispatch_on_cpu_emulation(monkeypatch):
     rel_dist = rel_pos.norm(dim=-1)
     inp = {str(d): torch.randn(b, n, C, 2 * d + 1) for d in range(L + 1)}
 
-    class FakePlan:
-        pairs, pair_base, pair_rows = [], [], []
-
-    basis = (torch.zeros(0), FakePlan(), M.Geometry(rel_pos, L))
+    E = b * n * k
+    Bo = O.get_basis(rel_pos.reshape(E, 3).double().numpy(), L)
+    monkeypatch.setattr(ops, 'basis_pairs', lambda flat, plan, E_: {(di, do): torch.from_numpy(np.asarray(Bo[f'{di},{do}'])).reshape(-1)
+                                                                     for di in range(L + 1) for do in range(L + 1)})
+    basis = (torch.zeros(0), None, M.Geometry(rel_pos, L))
     nmask = torch.ones(b, n, k, dtype=torch.bool)
     with torch.no_grad():
         out = M.conv_forward([conv], inp, (idx, nmask, None), rel_dist, basis)[0]
 
     # reference order of operations in float64
-    E = b * n * k
-    Bo = O.get_basis(rel_pos.reshape(E, 3).double().numpy(), L)
     feat = rel_dist.reshape(E, 1).double()
     worst = 0.0
     for do in range(L + 1):
