@@ -64,6 +64,19 @@ class Fiber:
         return [(d, c, od[d]) for d, c in self.structure if d in od]
 
 
+def forward_only_guard(what, modules, tensors=()):
+    """The kernels have no backward.  Called with autograd recording and anything that wants a gradient,
+    they would silently return tensors cut off from the graph (radial weights and inputs without gradients, the torch glue
+    with): fail loudly instead.  SE3Transformer.forward itself runs under torch.no_grad()."""
+    if not torch.is_grad_enabled():
+        return
+    wants = any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors) or \
+        any(p.requires_grad for m in modules for p in m.parameters())
+    if wants:
+        raise RuntimeError(f'{what} is forward only (no backward kernels): call it under torch.no_grad() / torch.inference_mode(), '
+                           'or use the reference implementation for training')
+
+
 def residual_add(x, res):
     return {d: (t + res[d] if d in res else t) for d, t in x.items()}
 
@@ -232,6 +245,10 @@ class ConvSE3(nn.Module):
         if (di, do) not in pk['images']:
             pc = self.kernel_unary[f'({di},{do})']
             lin = pc.rp.net['6']
+            if lin.weight.numel() == 0:
+                raise RuntimeError(f'ConvSE3 pair ({di},{do}): the fp32 net.6 weights were released by pack_weights(free_master=True) and '
+                                   'only the low-rank image was kept, but this forward needs the direct (K = 128) image (low-rank path '
+                                   'switched off or not applicable); rebuild the model or pack with free_master=False')
             with torch.no_grad():
                 pk['images'][(di, do)] = ops.pack_w3(lin.weight, lin.bias, pc.nc_out, pc.nc_in, pc.num_freq)
         return pk['images'][(di, do)]
@@ -371,6 +388,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
     in a single sweep: the T blocks (gather x basis) are built once per (degree pair, edge chunk) and consumed by every
     convolution's fused pairwise kernel."""
     c0 = convs[0]
+    forward_only_guard('ConvSE3', convs, list(inp.values()) + [rel_dist])
     idx, nmask, _ = edge_info
     b, n, k = idx.shape
     E = b * n * k
@@ -390,9 +408,12 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         tc_ok = {pair: conv.tc_eligible(*pair) for pair in conv.pairs}
         # low-rank radial path (distance-only radial functions): U = G V with the pair's cached basis, K = r+1 <= 64
         lr, plan = {}, None
-        if conv.edge_dim == 0 and ops.lowrank_enabled(E) and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
+        if conv.free_master and pk.get('lr') is not None and not os.environ.get('SE3B200_NO_LOWRANK'):
+            plan = pk['lr']                         # built by pack_weights(max_distance=...) before the masters went away:
+                                                    # the only image there is, whatever the edge count
+        elif conv.edge_dim == 0 and ops.lowrank_enabled(E) and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
             if conv.free_master:
-                plan = pk.get('lr')                 # built by pack_weights(max_distance=...) before the masters went away
+                plan = pk.get('lr')
             else:
                 plan = conv.lowrank_plan(float(rel_dist.max()))      # cached; one host sync for the distance range
         if plan is not None and plan['pairs']:
@@ -605,6 +626,7 @@ class AttentionSE3(nn.Module):
 
     def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
         assert pos_emb is None, 'rotary embeddings are not part of the B200 hot path'
+        forward_only_guard('AttentionSE3', [self], list(features.values()))
         idx, nmask, _ = edge_info
         queries = self.to_q(features)
         k_idx = None
@@ -703,6 +725,8 @@ class SE3Transformer(nn.Module):
                            (rotary_rel_dist, 'rotary_rel_dist')):
             if flag:
                 raise NotImplementedError(f'{name}=True is outside the B200 hot path of this package')
+        if differentiable_coors:
+            raise NotImplementedError('differentiable_coors=True needs the backward pass; this package is forward only (SURVEY.md 8f row 4)')
         dim_in = default(dim_in, dim)
         self.dim_in = dim_in if isinstance(dim_in, tuple) else (dim_in,) * input_degrees
         self.dim = dim
@@ -786,6 +810,13 @@ class SE3Transformer(nn.Module):
                 neighbor_mask=None, global_feats=None):
         assert not (self.accept_global_feats ^ exists(global_feats)), 'you cannot pass in global features unless you init the class correctly'
         _mask = mask
+        # float64 models / inputs (reference tests/test_equivariance.py:228-258 runs under a float64 default dtype): the kernels
+        # compute in float32; parameters are converted once, inputs are cast, results are returned in the caller's dtype
+        out_dtype = coors.dtype if coors.dtype == torch.float64 else None
+        if any(p.dtype == torch.float64 for p in self.parameters()):
+            import warnings
+            warnings.warn('se3_transformer_pytorch_b200 computes in float32: converting the float64 parameters of this model to float32')
+            self.float()
         if self.output_degrees == 1:
             return_type = 0
         if exists(self.token_emb):
@@ -799,6 +830,10 @@ class SE3Transformer(nn.Module):
             feats = {'0': feats[..., None]}
         if torch.is_tensor(global_feats):
             global_feats = {'0': global_feats[..., None]}
+        if exists(global_feats):
+            global_feats = {k: v.float() for k, v in global_feats.items()}
+        if exists(edges) and edges.is_floating_point():
+            edges = edges.float()
         b, n, d = feats['0'].shape[:3]
         device = feats['0'].device
         if not coors.is_cuda:
@@ -885,6 +920,8 @@ class SE3Transformer(nn.Module):
             x = {k: (masked_mean_nodes(v, _mask) if exists(_mask) else v.mean(dim=1)) for k, v in x.items()}
         if '0' in x:
             x['0'] = x['0'].squeeze(dim=-1)
+        if exists(out_dtype):
+            x = {k: v.to(out_dtype) for k, v in x.items()}
         if exists(return_type):
             return x[str(return_type)]
         return x

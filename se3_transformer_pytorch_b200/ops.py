@@ -64,7 +64,8 @@ def lib():
 
 
 LAUNCHES = 0          # number of libse3b200 kernel launches issued by this process (bench.py reports it)
-PROFILE = None        # when a list: every launch appends (kernel, start_event, end_event, algorithmic flops, algorithmic bytes)
+PROFILE = None        # when a list: every launch appends (kernel, start_event, end_event, reference-formulation FLOPs,
+                      # algorithmic (unpadded) bytes, tag, issued tensor-core FLOPs (every pass counted), issued fp32 FMA FLOPs)
 
 
 def _check(rc):
@@ -77,9 +78,8 @@ def _check(rc):
 class _timed:
     """CUDA-event bracket on the launching stream around one kernel launch (only when PROFILE is enabled)."""
 
-    def __init__(self, name, flops=0, nbytes=0, tag='', executed=None):
-        self.name, self.flops, self.nbytes, self.tag = name, flops, nbytes, tag
-        self.executed = flops if executed is None else executed
+    def __init__(self, name, flops=0, nbytes=0, tag='', mma=0, fma=0):
+        self.name, self.flops, self.nbytes, self.tag, self.mma, self.fma = name, flops, nbytes, tag, mma, fma
 
     def __enter__(self):
         if PROFILE is not None:
@@ -91,7 +91,7 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.end.record()
-            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes, self.tag, self.executed))
+            PROFILE.append((self.name, self.start, self.end, self.flops, self.nbytes, self.tag, self.mma, self.fma))
         return False
 
 
@@ -135,7 +135,8 @@ def knn(coors, k, valid_radius, node_mask=None, neighbor_mask=None, sparse_adj=N
     rel_dist = torch.empty((b, n, k), dtype=torch.float32, device=coors.device)
     nm, nbm, sa = _u8(node_mask), _u8(neighbor_mask), _u8(sparse_adj)
     valid_radius = float(min(valid_radius, 3.0e38))
-    with torch.cuda.device(coors.device):
+    nbytes = 12 * b * n + 25 * b * n * k + sum(t.numel() for t in (nm, nbm, sa) if t is not None)
+    with torch.cuda.device(coors.device), _timed('knn', nbytes=nbytes):
         _check(lib().se3_knn_fwd(_p(coors), _p(nm), _p(nbm), _p(sa), b, n, k, valid_radius, int(bool(causal)),
                                  _p(idx), _p(mask), _p(rel_pos), _p(rel_dist), _stream()))
     return idx, mask.view(torch.bool), rel_pos, rel_dist
@@ -220,7 +221,7 @@ def basis_flat(rel_pos, max_degree):
     E = rel_pos.numel() // 3
     plan = BasisPlan.get(max_degree, rel_pos.device)
     out = torch.empty(plan.rows_per_edge * E, dtype=torch.float32, device=rel_pos.device)
-    with torch.cuda.device(rel_pos.device):
+    with torch.cuda.device(rel_pos.device), _timed('basis', nbytes=E * (12 + 4 * plan.rows_per_edge)):
         _check(lib().se3_basis_fwd(_p(rel_pos), E, max_degree, _p(plan.row_ptr), _p(plan.col), _p(plan.val),
                                    _p(plan.pair_row0), _p(plan.pair_base_t), len(plan.pairs), _p(out), _stream()))
     return out, plan
@@ -262,7 +263,8 @@ def radial_trunk(feat, params, num_pairs):
     feat = _f32(feat)
     E, in_dim = feat.shape
     g = torch.empty((num_pairs, E, RADIAL_MID), dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with torch.cuda.device(feat.device), _timed('radial_trunk', flops=2 * E * num_pairs * RADIAL_MID * (in_dim + RADIAL_MID),
+                                                 nbytes=4 * (feat.numel() + params.numel() + g.numel())):
         _check(lib().se3_radial_trunk_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(g), _stream()))
     return g
 
@@ -287,8 +289,9 @@ def tbuild(x, idx, basis_pair, d_in, d_out, tile_begin=0, tile_count=None, out=N
     numel = t_numel(tile_count, Ci, F, P)
     if out is None or out.numel() < numel:
         out = torch.empty(numel, dtype=torch.float32, device=x.device)
-    nbytes = 4 * (numel + E * P * Q * F + E * Ci * Q) + 8 * E
-    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * F * P * Q, nbytes=nbytes):
+    Ec = min(E - tile_begin * TILE_E, tile_count * TILE_E)       # edges of this call; bytes WITHOUT the layout padding of T
+    nbytes = 4 * Ec * (Ci * F * P + P * Q * F + Ci * Q) + 8 * Ec
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * Ec * Ci * F * P * Q, nbytes=nbytes):
         _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(basis_pair), b, n, k, Ci, P, Q, F, tile_begin, tile_count,
                                     _p(out), _stream()))
     return out
@@ -316,8 +319,9 @@ def gather_tiles(x, idx, tile_begin=0, tile_count=None, out=None):
     numel = t_numel(tile_count, Ci, 1, Q)
     if out is None or out.numel() < numel:
         out = torch.empty(numel, dtype=torch.float32, device=x.device)
-    nbytes = 4 * (numel + E * Ci * Q) + 8 * E
-    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * Q * Q, nbytes=nbytes):
+    Ec = min(E - tile_begin * TILE_E, tile_count * TILE_E)
+    nbytes = 4 * Ec * (2 * Ci * Q) + 8 * Ec
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * Ec * Ci * Q * Q, nbytes=nbytes):
         _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(eye), b, n, k, Ci, Q, Q, 1, tile_begin, tile_count, _p(out), _stream()))
     return out
 
@@ -336,8 +340,9 @@ def tbuild_blocks(x, idx, blocks, P, F, tile_begin=0, tile_count=None, out=None)
     numel = t_numel(tile_count, Ci, F, P)
     if out is None or out.numel() < numel:
         out = torch.empty(numel, dtype=torch.float32, device=x.device)
-    nbytes = 4 * (numel + E * P * Q * F + E * Ci * Q) + 8 * E
-    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * E * Ci * F * P * Q, nbytes=nbytes):
+    Ec = min(E - tile_begin * TILE_E, tile_count * TILE_E)
+    nbytes = 4 * Ec * (Ci * F * P + P * Q * F + Ci * Q) + 8 * Ec
+    with torch.cuda.device(x.device), _timed('tbuild', flops=2 * Ec * Ci * F * P * Q, nbytes=nbytes):
         _check(lib().se3_tbuild_fwd(_p(x), _p(idx.contiguous()), _p(blocks), b, n, k, Ci, P, Q, F, tile_begin, tile_count, _p(out), _stream()))
     return out
 
@@ -359,13 +364,13 @@ def rotate_back(parts, D, E, Co, lo, out):
     ptrs = [(_p(t) if t is not None else None) for t in (list(parts) + [None] * 4)[:4]]
     P = 2 * lo + 1
     nbytes = 4 * (2 * E * Co * P + E * P * P)
-    with torch.cuda.device(out.device), _timed('fold_basis', flops=2 * E * Co * P * P, nbytes=nbytes):
+    with torch.cuda.device(out.device), _timed('rotate_back', flops=2 * E * Co * P * P, nbytes=nbytes):
         _check(lib().se3_rotate_back_fwd(*ptrs, _p(D), E, Co, lo, _p(out), _stream()))
 
 
 def pairwise_simt(g, W3, b3, T, E, Co, Ci, F, P, out, accumulate):
     _require_cuda(g, W3, b3, T, out)
-    with torch.cuda.device(out.device), _timed('pairwise_simt', flops=2 * E * Co * Ci * F * (RADIAL_MID + P)):
+    with torch.cuda.device(out.device), _timed('pairwise_simt', flops=2 * E * Co * Ci * F * (RADIAL_MID + P), fma=2 * E * Co * Ci * F * (RADIAL_MID + P)):
         _check(lib().se3_pairwise_simt_fwd(_p(g), _p(W3), _p(b3), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
 
 
@@ -388,8 +393,9 @@ def pairwise_tc(g, w_img, T, E, Co, Ci, F, P, out, accumulate, dump=None):
     _require_cuda(g, w_img, T, out)
     # algorithmic work: the radial GEMM (2*128 per R element) + the contraction with T (2*P per R element)
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + P)
-    nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
-    with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}'):
+    nbytes = w_img.numel() + 4 * E * Ci * F * P + 4 * E * Co * P * (2 if accumulate else 1)
+    with torch.cuda.device(out.device), _timed('pairwise_tc', flops=flops, nbytes=nbytes, tag=f'P{P}F{F}Ci{Ci}Co{Co}',
+                                               mma=2 * E * Co * Ci * F * 3 * RADIAL_MID, fma=2 * E * Co * Ci * F * P):
         if dump is None:
             _check(lib().se3_pairwise_tc_fwd(_p(g), _p(w_img), _p(T), E, Co, Ci, F, P, int(accumulate), _p(out), _stream()))
         else:
@@ -419,10 +425,11 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, o
     flops = 2 * E * Co * Ci * F * (RADIAL_MID + (alg_P if alg_P is not None else P))
     if alg_units is not None:
         flops = E * Co * Ci * alg_units
-    executed = 2 * E * Co * Ci * F * (3 * Kp + P)          # issued: 3 fp16 MMA passes of K = Kp + P fp32 FMAs per R element
-    nbytes = w_img.numel() + 4 * t_numel((E + TILE_E - 1) // TILE_E, Ci, F, P) + 4 * E * Co * P * (2 if accumulate else 1)
+    # issued: 3 fp16 MMA passes of K = Kp per R element on the tensor cores, P fp32 FMAs per R element on the SIMT pipe
+    nbytes = w_img.numel() + 4 * E * Ci * F * P + 4 * E * Co * P * (2 if accumulate else 1)
     tag = f'P{P}F{F}Ci{Ci}Co{Co}K{Kp}' + (f'(in-side of P{alg_P})' if alg_P is not None else '')
-    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=tag, executed=executed):
+    with torch.cuda.device(out.device), _timed('pairwise_lr', flops=flops, nbytes=nbytes, tag=tag,
+                                               mma=2 * E * Co * Ci * F * 3 * Kp, fma=2 * E * Co * Ci * F * P):
         if out_strides is None:
             _check(lib().se3_pairwise_lr_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out), _stream()))
         else:
@@ -477,7 +484,7 @@ def pool(x, mask):
     b, n, k = x.shape[:3]
     C = x[0, 0, 0].numel()
     out = torch.empty((b, n) + tuple(x.shape[3:]), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed('pool', nbytes=4 * (x.numel() + out.numel()) + b * n * k):
         _check(lib().se3_pool_fwd(_p(x), _p(_u8(mask)), b * n, k, C, _p(out), _stream()))
     return out
 
