@@ -140,6 +140,55 @@ int se3_fold_basis_cm_fwd(const float* S, const float* basis_pair, int64_t E, in
 int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int64_t E, int Co, int Ci, int F, int P,
                           int Kp, int accumulate, float* out, unsigned long long* trace, void* stream);
 
+/* ---- production path of distance-only radial functions: low-rank radial basis + edge-aligned frames as one GEMM per
+ * (degree_out, |m|) (the same product S:237-254, 326-343 re-associated) ------------------------------------ */
+
+/* Radial trunk as se3_radial_trunk_fwd, followed in the same kernel by the low-rank radial coordinates of every pair:
+ *   out_U [num_pairs, E, 64]: columns 0..r-1 = g V, column r = 1 (bias slot), rest 0, r = ones_col[pair], V [num_pairs,128,64]
+ *   (columns >= r zero);  stats [num_pairs, 2] (caller zeroes it): (max |g - U V^T|, max |g|) over the edges, accumulated with
+ *   atomicMax -- the run-time check that the cached basis covers this forward's distances, read by the host once per forward.
+ *   out_g may be NULL. */
+int se3_radial_trunk_u_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params, const float* V,
+                           const int* ones_col, float* out_g, float* out_U, float* stats, void* stream);
+
+/* Per-edge frames: R_e takes the polar axis a = (0,1,0) of the reference's harmonics (basis.py:57-95) to the direction of
+ * rel_pos[e]; D_out[l] [E, 2l+1, 2l+1] = real Wigner matrix D_l(R_e) in the reference's basis, l = 1..lmax <= 5, computed in
+ * float64 as Y_l(R x_s) pinv(Y_l(x_s)) from the tables xs[l] [n_samples[l], 3] / pin[l] [2l+1, n_samples[l]] (device, float64).
+ * xs, pin, n_samples, D_out: HOST arrays indexed by l (entry 0 unused). */
+int se3_frames_fwd(const float* rel_pos, int64_t E, int lmax, const double* const* xs, const double* const* pin,
+                   const int* n_samples, float* const* D_out, void* stream);
+
+/* Neighbour gather (S:237-238, utils.py:56-70) fused with the rotation into the edge frame:
+ *   X[tile][i][n][edge_local] = sum_q D[e][q][n] * x[b, idx[e], i, q],   x [b,n,Ci,Q], D [E,Q,Q] (NULL for Q = 1),
+ * for the edge tiles [tile_begin, tile_begin + tile_count) of 128 edges (rows past E are zero). */
+int se3_rotgather_fwd(const float* x, const int64_t* idx, const float* D, int b, int n, int k, int Ci, int Q,
+                      int64_t tile_begin, int64_t tile_count, float* X, void* stream);
+
+/* out[row] = max_c |x[row, c]| (combine != 0: max with the value already in out); x [rows, W]. */
+int se3_rowabsmax_fwd(const float* x, int64_t rows, int W, int combine, float* out, void* stream);
+/* sx[e] = power of two with nodemax[b(e), idx[e]] * sqrt(2 max_degree + 1) * sx[e] < 2^10 (1 for all-zero nodes). */
+int se3_edge_scale_fwd(const float* nodemax, const int64_t* idx, int b, int n, int k, int max_degree, float* sx, void* stream);
+
+/* One K segment of se3_zgemm_fwd: radial coordinates U (row stride 64 floats; the segment uses the 16 columns at the pointer),
+ * rotated neighbour features X from se3_rotgather_fwd ([tiles][Ci][ncomp][128]) and the component indices read from it. */
+typedef struct se3_zseg {
+  const float* U;
+  const float* X;
+  int Ci, ncomp, cplus, cminus;
+} se3_zseg;
+
+/* out'[e, plane c, o] = sum over segments, i, f, k of  Z_c[e,(seg,i,f,k)] * F'[o,(seg,i,f,k)]   with
+ *   mode 1 (|m| = 0):  Z = U[e,k] x'[e,i,cplus]                                    (one plane, F = 1)
+ *   mode 2 (|m| > 0):  Z_+ = (f=a: U x'[cplus], f=b: -U x'[cminus]),  Z_- = (f=a: U x'[cminus], f=b: U x'[cplus])   (two planes)
+ * on the tcgen05 tensor cores, Z generated on the fly into tensor memory (3-pass fp16 split, fp32 partial sums drained every
+ * flush_stages (0 = default) stages of 64 K values).  w_img: se3_zgemm_pack of every segment in order.  Co % 128 == 0,
+ * (Ci * mode) % 4 == 0, <= 16 segments (HOST array).  out rows: edge stride out_edge_stride floats, plane c at comp_off{c}. */
+int     se3_zgemm_tile_n(int Co, int mode);
+int64_t se3_zgemm_image_bytes(int Co, int mode, int total_stages);
+int se3_zgemm_pack(const float* Fp, int Kp, int col0, int Co, int CiF, int mode, int total_stages, int stage0, void* image, void* stream);
+int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img, const float* sx, int64_t E, int Co, int mode,
+                  float* out, int64_t out_edge_stride, int comp_off0, int comp_off1, int flush_stages, void* stream);
+
 /* Masked mean over the neighbour axis (utils.py:72-80): x [B, K, C] , mask [B, K] (NULL = plain mean) -> out [B, C]. */
 int se3_pool_fwd(const float* x, const uint8_t* mask, int64_t B, int K, int64_t C, float* out, void* stream);
 

@@ -145,7 +145,14 @@ def aligned_coeffs(li, lo):
 class EdgeFrames:
     """Per-forward geometry of the aligned formulation: D_l per edge and the tbuild blocks derived from them."""
 
-    def __init__(self, rel_pos, lmax):
+    def __init__(self, rel_pos, lmax, D=None):
+        if D is not None:
+            # Wigner matrices already built on the device (ops.frames -> se3_frames_fwd, the production path); this class then
+            # only derives the tbuild blocks of the R-first kernels from them
+            self.E = rel_pos.numel() // 3
+            self.D = [torch.ones((self.E, 1, 1), dtype=torch.float32, device=rel_pos.device)] + list(D[1:])
+            self._blocks = {}
+            return
         d = rel_pos.reshape(-1, 3).double()
         nrm = d.norm(dim=-1, keepdim=True)
         # coincident points: the reference evaluates its harmonics at beta = atan2(0, 0) = 0, alpha = 0 (B:57-95), which is

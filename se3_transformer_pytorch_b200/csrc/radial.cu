@@ -102,7 +102,138 @@ radial_trunk_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const
   for (int e = 0; e < ne; ++e) og[(size_t)e * kMid + t] = h[e][t];
 }
 
+// Trunk + low-rank radial coordinates: the same trunk, followed in the same CTA by
+//   U[e, 0..r-1] = g[e,:] V[:, 0..r-1],   U[e, r] = 1 (bias slot),   U[e, r+1..63] = 0
+// with the pair's cached orthonormal basis V [128, 64] (columns >= r are zero), and by the check of that basis on the edges of
+// THIS forward: stats[pair] = (max |g - U V^T|, max |g|) accumulated with atomicMax (non-negative floats order like their bit
+// patterns), read by the host once per forward.  g itself is only written when out_g != NULL.
+constexpr int kVPad = 65;
+
+__global__ void __launch_bounds__(128)
+radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const float* __restrict__ params, int64_t param_stride,
+                      const float* __restrict__ Vall, const int* __restrict__ ones_col, float* __restrict__ out_g,
+                      float* __restrict__ out_U, float* __restrict__ stats) {
+  extern __shared__ __align__(16) float dsm[];
+  float (*h)[kMid + 4] = reinterpret_cast<float (*)[kMid + 4]>(dsm);                    // [32][132]
+  float (*fs)[64] = reinterpret_cast<float (*)[64]>(dsm + kTrunkEB * (kMid + 4));       // [32][64]; reused for U
+  float* Vs = dsm + kTrunkEB * (kMid + 4) + kTrunkEB * 64;                               // [128][65]
+  const int pair = blockIdx.y;
+  const int64_t e0 = (int64_t)blockIdx.x * kTrunkEB;
+  const int ne = (int)max((int64_t)0, min((int64_t)kTrunkEB, E - e0));
+  const int t = threadIdx.x;
+  const float* P = params + (size_t)pair * param_stride;
+  const float* W1T = P;
+  const float* b1 = W1T + (size_t)in_dim * kMid;
+  const float* ln1w = b1 + kMid;
+  const float* ln1b = ln1w + kMid;
+  const float* W2T = ln1b + kMid;
+  const float* b2 = W2T + kMid * kMid;
+  const float* ln2w = b2 + kMid;
+  const float* ln2b = ln2w + kMid;
+  const int rcol = ones_col[pair];                 // r: the bias slot; the basis has r columns
+
+  for (int idx = t; idx < ne * in_dim; idx += 128) fs[idx / in_dim][idx % in_dim] = feat[(e0 + idx / in_dim) * in_dim + idx % in_dim];
+  for (int idx = t; idx < kMid * 64; idx += 128) Vs[(idx >> 6) * kVPad + (idx & 63)] = Vall[(size_t)pair * kMid * 64 + idx];
+  __syncthreads();
+  {
+    float acc[kTrunkEB];
+    const float bias = b1[t];
+#pragma unroll
+    for (int e = 0; e < kTrunkEB; ++e) acc[e] = bias;
+    for (int d = 0; d < in_dim; ++d) {
+      const float w = W1T[d * kMid + t];
+#pragma unroll
+      for (int e = 0; e < kTrunkEB; ++e) acc[e] = fmaf(fs[e][d], w, acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < kTrunkEB; ++e) h[e][t] = acc[e];
+  }
+  __syncthreads();
+  ln_gelu_rows(h, ne, ln1w, ln1b);
+  __syncthreads();
+  {
+    float acc[kTrunkEB];
+    const float bias = b2[t];
+#pragma unroll
+    for (int e = 0; e < kTrunkEB; ++e) acc[e] = bias;
+    for (int c = 0; c < kMid; c += 4) {
+      const float w0 = W2T[(c + 0) * kMid + t], w1 = W2T[(c + 1) * kMid + t];
+      const float w2 = W2T[(c + 2) * kMid + t], w3 = W2T[(c + 3) * kMid + t];
+#pragma unroll
+      for (int e = 0; e < kTrunkEB; ++e) {
+        const float4 a = *reinterpret_cast<const float4*>(&h[e][c]);
+        acc[e] = fmaf(a.x, w0, acc[e]);
+        acc[e] = fmaf(a.y, w1, acc[e]);
+        acc[e] = fmaf(a.z, w2, acc[e]);
+        acc[e] = fmaf(a.w, w3, acc[e]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kTrunkEB; ++e) h[e][t] = acc[e];
+  }
+  __syncthreads();
+  ln_gelu_rows(h, ne, ln2w, ln2b);
+  __syncthreads();
+  if (out_g != nullptr) {
+    float* og = out_g + ((size_t)pair * E + e0) * kMid;
+    for (int e = 0; e < ne; ++e) og[(size_t)e * kMid + t] = h[e][t];
+  }
+  // U = g V: thread t -> column k = t % 64 for 16 of the 32 edges
+  {
+    const int k = t & 63, eh = (t >> 6) * 16;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    if (k < rcol) {
+      for (int j = 0; j < kMid; ++j) {
+        const float v = Vs[j * kVPad + k];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = fmaf(h[eh + e][j], v, acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) fs[eh + e][k] = acc[e];
+  }
+  __syncthreads();
+  // residual of the cached basis on these edges: thread t = hidden unit
+  float rmax = 0.f, gmax = 0.f;
+  for (int e = 0; e < ne; ++e) {
+    float rec = 0.f;
+    for (int k = 0; k < rcol; ++k) rec = fmaf(fs[e][k], Vs[t * kVPad + k], rec);
+    const float gv = h[e][t];
+    rmax = fmaxf(rmax, fabsf(gv - rec));
+    gmax = fmaxf(gmax, fabsf(gv));
+  }
+  rmax = warp_max(rmax);
+  gmax = warp_max(gmax);
+  if ((t & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned int*>(stats + 2 * pair), __float_as_uint(rmax));
+    atomicMax(reinterpret_cast<unsigned int*>(stats + 2 * pair + 1), __float_as_uint(gmax));
+  }
+  float* ou = out_U + ((size_t)pair * E + e0) * 64;
+  for (int idx = t; idx < ne * 64; idx += 128) {
+    const int e = idx >> 6, k = idx & 63;
+    ou[idx] = (k == rcol) ? 1.f : fs[e][k];
+  }
+}
+
 }  // namespace se3
+
+extern "C" int se3_radial_trunk_u_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params, const float* V,
+                                      const int* ones_col, float* out_g, float* out_U, float* stats, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(E > 0 && num_pairs > 0, "se3_radial_trunk_u_fwd: bad sizes");
+  SE3_REQUIRE(in_dim >= 1 && in_dim <= 64, "se3_radial_trunk_u_fwd: in_dim %d unsupported (1..64)", in_dim);
+  SE3_REQUIRE(V != nullptr && ones_col != nullptr && out_U != nullptr && stats != nullptr, "se3_radial_trunk_u_fwd: null pointer");
+  const int64_t param_stride = (int64_t)in_dim * kMid + 3 * kMid + kMid * kMid + 3 * kMid;
+  const size_t smem = sizeof(float) * (kTrunkEB * (kMid + 4) + kTrunkEB * 64 + kMid * kVPad);
+  SE3_CUDA_OK(cudaFuncSetAttribute(radial_trunk_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(E, kTrunkEB), (unsigned)num_pairs);
+  radial_trunk_u_kernel<<<grid, 128, smem, as_stream(stream)>>>(feat, E, in_dim, params, param_stride, V, ones_col, out_g, out_U, stats);
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
 
 extern "C" int se3_radial_trunk_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params,
                                     float* out_g, void* stream) {

@@ -1,0 +1,474 @@
+// K4z: the fused pairwise kernel of the production path (low-rank radial basis + edge-aligned frames) as ONE
+// tensor-core GEMM per (degree_out, |m|) with the A operand generated on the fly.
+//
+// In the edge-aligned frame the output component m of degree lo of one ConvSE3 is
+//     m = 0 :  out'[e,o]   = sum_{li} sum_i  w0[e,o,i]  x'_li[e,i,0]
+//     m > 0 :  out'[e,o,+] = sum_{li>=m} sum_i  a[e,o,i] x'[e,i,+m] - b[e,o,i] x'[e,i,-m]
+//              out'[e,o,-] = sum_{li>=m} sum_i  b[e,o,i] x'[e,i,+m] + a[e,o,i] x'[e,i,-m]
+// (reference S:237-254, 326-343 re-associated), and every radial weight is a short dot product with the per-edge radial
+// coordinates U of its degree pair, w[e,o,i] = sum_k U[e,k] F'[(o,i),k] (K = r+1 <= 16 per sub-segment).
+// Instead of forming w (R-first: a K = 16 GEMM per radial weight tile, then 2 fp32 FMAs per weight on the SIMT pipe, a TMEM
+// read of every weight and a hand-off per tile) the sums are exchanged:
+//     out'[e,o,c] = sum_{(li,i,f,k)}  Z_c[e,(li,i,f,k)] * F'[o,(li,i,f,k)],        Z_c[e,(li,i,f,k)] = +-U_li[e,k] x'_li[e,i,+-m]
+// one GEMM with M = edges, N = output channels, K = sum_li C_in * F * 16, whose A operand Z is an outer product per edge:
+// it costs E*C_in*16 multiplies to make (C_out times fewer than there are radial weights) and is produced by the CUDA cores
+// straight into tensor memory, split x = hi + lo in fp16 for the 3-pass fp32-parity MMA (hi*hi + lo*hi + hi*lo).  The
+// accumulator stays in tensor memory over the whole K loop; nothing per radial weight ever touches the SIMT pipe.
+//
+// CTA = 128 edges x N channels (MODE 1: one component, N = 256 or 128; MODE 2: components (+m, -m), N = 128, two
+// accumulators fed by the same B tiles).  384 threads: warp 0 streams the weight image (TMA bulk copies, 2-CTA multicast),
+// warp 1 issues tcgen05.mma (.ts form: A from tensor memory), warps 4-11 generate Z (one warp per TMEM lane quarter and stage
+// parity) and own the fp32 partial sums: tensor-core accumulation rounds toward zero, so every `flush_stages` stages the
+// accumulator is drained into registers (round-to-nearest adds) and restarted.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace se3 {
+
+constexpr int kZThreads = 384;
+constexpr int kZMaxSeg = 16;
+constexpr uint32_t kZTmemCols = 512;
+constexpr uint32_t kZACol = 256;              // D: columns [0, 256); A ring: columns [256, 512)
+constexpr uint32_t kZWRingBytes = 196608;     // shared memory for the weight ring
+
+struct ZSeg {
+  const float* U;      // [E, 64] fp32 (this sub-segment reads columns 0..15 from the pointer given)
+  const float* X;      // rotated neighbour features [tiles][Ci][ncomp][128]
+  int Ci, ncomp, cplus, cminus, n_stage, pad;
+};
+
+struct ZParams {
+  ZSeg seg[kZMaxSeg];
+  int n_seg;
+  const uint8_t* w_img;      // [n_nt][S][hi: N x 128 B | lo: N x 128 B], SW128 K-major, 64 K values (4 chunks) per stage
+  const float* sx;           // [E] power-of-two scale of the edge's neighbour features (keeps Z inside the fp16 range)
+  float* out;
+  int64_t E;
+  int64_t out_es;            // floats per edge row of out
+  int comp_off[2];           // offset of the component plane(s) inside an edge row
+  int n_mt, n_nt, S, flush_stages;
+};
+
+__device__ __forceinline__ void z_split16(const float (&p)[16], uint32_t (&r)[16]) {
+  // 16 fp32 -> 8 packed fp16 pairs hi (r[0..7]) + 8 packed pairs lo (r[8..15]); element 2c in the low half
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const __half2 h = __floats2half2_rn(p[2 * c], p[2 * c + 1]);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(p[2 * c] - hf.x, p[2 * c + 1] - hf.y);
+    r[c] = *reinterpret_cast<const uint32_t*>(&h);
+    r[8 + c] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+template <int MODE, int N, int CSZ>
+__global__ void __launch_bounds__(kZThreads, 1)
+zgemm_kernel(const __grid_constant__ ZParams prm) {
+  static_assert(MODE == 1 || (MODE == 2 && N == 128), "MODE 2 uses two N = 128 accumulators");
+  constexpr int DCOLS = (MODE == 2) ? 256 : N;            // accumulator columns in use
+  constexpr int ACC = DCOLS / 2;                          // per flush thread
+  constexpr int ASLOT = (MODE == 2) ? 128 : 64;           // TMEM columns of one A stage
+  constexpr int AS = 256 / ASLOT;                         // A ring depth (stages)
+  constexpr uint32_t kStageBytes = 2u * N * 128u;
+  constexpr int WS = kZWRingBytes / kStageBytes;          // W ring depth (stages)
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sW = base;
+  const uint32_t sBar = sW + WS * kStageBytes;
+  const uint32_t bar_w_full = sBar;
+  const uint32_t bar_w_empty = bar_w_full + 8 * WS;
+  const uint32_t bar_a_full = bar_w_empty + 8 * WS;
+  const uint32_t bar_a_empty = bar_a_full + 8 * AS;
+  const uint32_t bar_d_full = bar_a_empty + 8 * AS;
+  const uint32_t bar_d_empty = bar_d_full + 8;
+  const uint32_t s_tmem_slot = bar_d_empty + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t crank = (CSZ > 1) ? cluster_ctarank() : 0u;
+  const int S = prm.S, FS = prm.flush_stages;
+  // cluster = CSZ consecutive edge tiles of one channel tile (they share every weight stage); channel tile fastest
+  const int64_t cid = blockIdx.x / CSZ;
+  const int nt = (int)(cid % prm.n_nt);
+  int64_t mt = (cid / prm.n_nt) * CSZ + crank;
+  const bool active = mt < prm.n_mt;
+  if (!active) mt = prm.n_mt - 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WS; ++s) {
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, CSZ);
+    }
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(bar_a_full + 8 * s, 4);
+      mbar_init(bar_a_empty + 8 * s, 1);
+    }
+    mbar_init(bar_d_full, 1);
+    mbar_init(bar_d_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kZTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CSZ > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== weight producer =====================
+      const uint8_t* wsrc = prm.w_img + (size_t)nt * S * kStageBytes;
+      constexpr uint32_t kShare = kStageBytes / CSZ;
+      for (int s = 0; s < S; ++s) {
+        const int slot = s % WS;
+        const uint32_t ph = (uint32_t)(s / WS) & 1u;
+        mbar_wait(bar_w_empty + 8 * slot, ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kStageBytes);
+          if (CSZ == 1) {
+            bulk_g2s(sW + slot * kStageBytes, wsrc + (size_t)s * kStageBytes, kStageBytes, bar_w_full + 8 * slot);
+          } else {
+            bulk_g2s_mc(sW + slot * kStageBytes + crank * kShare, wsrc + (size_t)s * kStageBytes + crank * kShare, kShare,
+                        bar_w_full + 8 * slot, kMask);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      int blk_start = 0, blk = 0;
+      for (int s = 0; s < S; ++s) {
+        const int wslot = s % WS, aslot = s % AS;
+        if (s == blk_start && blk > 0) {
+          mbar_wait(bar_d_empty, (uint32_t)(blk - 1) & 1u);          // the previous block has been drained into registers
+        }
+        mbar_wait(bar_w_full + 8 * wslot, (uint32_t)(s / WS) & 1u);
+        mbar_wait(bar_a_full + 8 * aslot, (uint32_t)(s / AS) & 1u);
+        tc_fence_after();
+        const uint32_t wb = sW + wslot * kStageBytes;
+        const bool last_of_blk = (s + 1 == S) || (s + 1 == blk_start + FS);
+        if (elect_one()) {
+          if (MODE == 1) {
+            uint32_t accum = (s == blk_start) ? 0u : 1u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
+              const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
+              const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+              tc_mma_f16_ts(tmem_base, a_hi, b_hi, kIdesc, accum);
+              tc_mma_f16_ts(tmem_base, a_hi + 8, b_hi, kIdesc, 1u);
+              tc_mma_f16_ts(tmem_base, a_hi, b_lo, kIdesc, 1u);
+              accum = 1u;
+            }
+          } else {
+#pragma unroll
+            for (int comp = 0; comp < 2; ++comp) {
+              uint32_t accum = (s == blk_start) ? 0u : 1u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + comp * 64 + c * 16);
+                const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
+                const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+                const uint32_t d = tmem_base + (uint32_t)(comp * 128);
+                tc_mma_f16_ts(d, a_hi, b_hi, kIdesc, accum);
+                tc_mma_f16_ts(d, a_hi + 8, b_hi, kIdesc, 1u);
+                tc_mma_f16_ts(d, a_hi, b_lo, kIdesc, 1u);
+                accum = 1u;
+              }
+            }
+          }
+          if (CSZ == 1) tc_commit(bar_w_empty + 8 * wslot);
+          else tc_commit_mc(bar_w_empty + 8 * wslot, kMask);
+          tc_commit(bar_a_empty + 8 * aslot);
+          if (last_of_blk) tc_commit(bar_d_full);
+        }
+        __syncwarp();
+        if (last_of_blk) { blk_start = s + 1; ++blk; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===================== Z generators + fp32 partial sums =====================
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int h = (warp - 4) >> 2;             // stage parity generated by this warp / accumulator half drained by it
+    const int el = q * 32 + lane;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    const int64_t eg = mt * SE3_TILE_E + el;
+    const bool live = eg < prm.E;
+    const float sxe = live ? prm.sx[eg] : 1.f;
+
+    float acc[ACC];
+#pragma unroll
+    for (int j = 0; j < ACC; ++j) acc[j] = 0.f;
+    int flushed = 0;                           // accumulation blocks drained so far
+    const int n_blk = (S + FS - 1) / FS;
+
+    auto drain = [&]() {
+      mbar_wait(bar_d_full, (uint32_t)flushed & 1u);
+      tc_fence_after();
+      const uint32_t c0 = tmem_base + t_lane + (uint32_t)(h * ACC);
+#pragma unroll
+      for (int t = 0; t < ACC / 32; ++t) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(c0 + (uint32_t)(t * 32), ra);
+        tmem_ld16(c0 + (uint32_t)(t * 32 + 16), rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          acc[t * 32 + j] += __uint_as_float(ra[j]);
+          acc[t * 32 + 16 + j] += __uint_as_float(rb[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d_empty);
+      ++flushed;
+    };
+
+    // position of this warp's next stage: (segment, local stage)
+    int seg = 0, sl = h;
+    while (seg < prm.n_seg && sl >= prm.seg[seg].n_stage) { sl -= prm.seg[seg].n_stage; ++seg; }
+    int s = h;                                 // global stage index
+    int cur_seg = -1;
+    float us[16];
+    const float* Xp = nullptr;                 // component row(s) of this thread inside the current segment's X
+    int xstride = 0, cp = 0, cm = 0, Ci = 0;
+
+    auto load_x = [&](int sg, int stage_local, float (&xv)[4]) {
+      const ZSeg& z = prm.seg[sg];
+      const float* xb = z.X + ((size_t)mt * z.Ci * z.ncomp) * 128 + el;
+      if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = stage_local * 4 + c;
+          xv[c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int il = 0; il < 2; ++il) {
+          const int i = stage_local * 2 + il;
+          xv[2 * il] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
+          xv[2 * il + 1] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
+        }
+      }
+    };
+    (void)Xp; (void)xstride; (void)cp; (void)cm; (void)Ci;
+
+    float xv[4] = {0.f, 0.f, 0.f, 0.f}, xn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (seg < prm.n_seg) load_x(seg, sl, xv);
+    while (seg < prm.n_seg) {
+      // next stage of this warp (two global stages ahead): prefetch its neighbour features
+      int nseg = seg, nsl = sl + 2;
+      while (nseg < prm.n_seg && nsl >= prm.seg[nseg].n_stage) { nsl -= prm.seg[nseg].n_stage; ++nseg; }
+      if (nseg < prm.n_seg) load_x(nseg, nsl, xn);
+      if (seg != cur_seg) {
+        const float4* urow = reinterpret_cast<const float4*>(prm.seg[seg].U + (size_t)(live ? eg : 0) * 64);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 u4 = live ? __ldg(urow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          us[4 * v + 0] = u4.x * sxe; us[4 * v + 1] = u4.y * sxe; us[4 * v + 2] = u4.z * sxe; us[4 * v + 3] = u4.w * sxe;
+        }
+        cur_seg = seg;
+      }
+      // drain every accumulation block that ended at least AS stages ago (the MMA warp cannot run further ahead anyway)
+      while (flushed < n_blk && min((flushed + 1) * FS, S) - 1 <= s - AS) drain();
+      const int aslot = s % AS;
+      mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(s / AS) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT);
+      if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[c];
+          uint32_t r[16];
+          z_split16(p, r);
+          tmem_st16(a0 + (uint32_t)(c * 16), r);
+        }
+      } else {
+#pragma unroll
+        for (int il = 0; il < 2; ++il) {
+          float p[16];
+          uint32_t rP[16], rM[16], nM[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[2 * il];
+          z_split16(p, rP);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[2 * il + 1];
+          z_split16(p, rM);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nM[j] = rM[j] ^ 0x80008000u;
+          // component +m: (f = a: U x+), (f = b: -U x-);   component -m: (f = a: U x-), (f = b: U x+)
+          tmem_st16(a0 + (uint32_t)((2 * il) * 16), rP);
+          tmem_st16(a0 + (uint32_t)((2 * il + 1) * 16), nM);
+          tmem_st16(a0 + (uint32_t)(64 + (2 * il) * 16), rM);
+          tmem_st16(a0 + (uint32_t)(64 + (2 * il + 1) * 16), rP);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xv[c] = xn[c];
+      seg = nseg; sl = nsl; s += 2;
+    }
+    while (flushed < n_blk) drain();
+
+    // out'[e, component plane, channels of this tile]
+    if (active && live) {
+      const float inv = 1.f / sxe;
+      float* dst;
+      if (MODE == 1) dst = prm.out + (size_t)eg * prm.out_es + prm.comp_off[0] + (size_t)nt * N + h * ACC;
+      else dst = prm.out + (size_t)eg * prm.out_es + prm.comp_off[h] + (size_t)nt * N;
+#pragma unroll
+      for (int j = 0; j < ACC; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CSZ > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kZTmemCols) : "memory");
+  }
+}
+
+// Weight image of one sub-segment: rows (o, i, f) of Fp (columns [col0, col0+16) of each row) -> stages [stage0, stage0+n) of
+// the launch image.  Chunk c = i*F + f of the segment sits in stage c/4 at K columns [(c%4)*16, +16).
+__global__ void zpack_kernel(const float* __restrict__ Fp, int Kp, int col0, int Co, int CiF, int N, int S, int stage0, int n_stage,
+                             uint8_t* __restrict__ img) {
+  const int nt = blockIdx.y, sl = blockIdx.x;
+  uint8_t* dst = img + ((size_t)nt * S + stage0 + sl) * (2u * N * 128u);
+  for (int t = threadIdx.x; t < N * 64; t += blockDim.x) {
+    const int r = t >> 6, k = t & 63;
+    const int c = sl * 4 + (k >> 4);
+    const int o = nt * N + r;
+    const float w = (c < CiF && o < Co) ? Fp[((size_t)o * CiF + c) * Kp + col0 + (k & 15)] : 0.f;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    const uint32_t off = (uint32_t)(r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + (size_t)N * 128 + off) = lo;
+  }
+}
+
+template <int MODE, int N, int CSZ>
+static int launch_z(const ZParams& prm, cudaStream_t s) {
+  constexpr uint32_t kStageBytes = 2u * N * 128u;
+  constexpr int WS = kZWRingBytes / kStageBytes;
+  const size_t smem = 1024 + (size_t)WS * kStageBytes + 512;
+  auto kern = zgemm_kernel<MODE, N, CSZ>;
+  SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_mg = (prm.n_mt + CSZ - 1) / CSZ;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_mg * prm.n_nt * CSZ));
+  cfg.blockDim = dim3(kZThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSZ;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SE3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prm));
+  return SE3_OK;
+}
+
+static int z_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace se3
+
+extern "C" int se3_zgemm_tile_n(int Co, int mode) {
+  if (Co <= 0 || Co % 128 != 0) return -1;
+  if (mode == 2) return 128;
+  if (mode != 1) return -1;
+  return (Co % 256 == 0) ? 256 : 128;
+}
+
+extern "C" int64_t se3_zgemm_image_bytes(int Co, int mode, int total_stages) {
+  const int N = se3_zgemm_tile_n(Co, mode);
+  if (N < 0 || total_stages <= 0) return -1;
+  return (int64_t)(Co / N) * total_stages * 2 * N * 128;
+}
+
+extern "C" int se3_zgemm_pack(const float* Fp, int Kp, int col0, int Co, int CiF, int mode, int total_stages, int stage0, void* image,
+                              void* stream) {
+  using namespace se3;
+  const int N = se3_zgemm_tile_n(Co, mode);
+  SE3_REQUIRE(N > 0, "se3_zgemm_pack: Co=%d must be a multiple of 128 (mode %d)", Co, mode);
+  SE3_REQUIRE(Fp != nullptr && image != nullptr, "se3_zgemm_pack: null pointer");
+  SE3_REQUIRE(Kp >= 16 && Kp % 16 == 0 && col0 >= 0 && col0 + 16 <= Kp, "se3_zgemm_pack: bad column range");
+  SE3_REQUIRE(CiF > 0, "se3_zgemm_pack: bad sizes");
+  const int n_stage = (int)ceil_div(CiF, 4);
+  SE3_REQUIRE(stage0 >= 0 && stage0 + n_stage <= total_stages, "se3_zgemm_pack: stage range outside the image");
+  zpack_kernel<<<dim3((unsigned)n_stage, (unsigned)(Co / N)), 256, 0, as_stream(stream)>>>(Fp, Kp, col0, Co, CiF, N, total_stages, stage0, n_stage,
+                                                                                         reinterpret_cast<uint8_t*>(image));
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img, const float* sx, int64_t E, int Co, int mode,
+                             float* out, int64_t out_edge_stride, int comp_off0, int comp_off1, int flush_stages, void* stream) {
+  using namespace se3;
+  const int N = se3_zgemm_tile_n(Co, mode);
+  SE3_REQUIRE(N > 0, "se3_zgemm_fwd: Co=%d must be a multiple of 128 and mode 1 or 2 (got %d)", Co, mode);
+  SE3_REQUIRE(E > 0 && n_seg >= 1 && n_seg <= kZMaxSeg, "se3_zgemm_fwd: bad sizes (1..%d segments)", kZMaxSeg);
+  SE3_REQUIRE(segs != nullptr && w_img != nullptr && sx != nullptr && out != nullptr, "se3_zgemm_fwd: null pointer");
+  SE3_REQUIRE(out_edge_stride >= Co && out_edge_stride % 4 == 0 && comp_off0 % 4 == 0 && comp_off1 % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0, "se3_zgemm_fwd: output rows must be 16-byte aligned");
+  ZParams prm;
+  prm.n_seg = n_seg;
+  int S = 0;
+  const int F = mode;          // MODE 1: one weight per (o,i); MODE 2: the pair (a, b)
+  for (int i = 0; i < n_seg; ++i) {
+    const se3_zseg& z = segs[i];
+    SE3_REQUIRE(z.U != nullptr && z.X != nullptr && z.Ci > 0 && z.ncomp >= 1 && z.cplus >= 0 && z.cplus < z.ncomp &&
+                z.cminus >= 0 && z.cminus < z.ncomp, "se3_zgemm_fwd: bad segment %d", i);
+    SE3_REQUIRE((z.Ci * F) % 4 == 0, "se3_zgemm_fwd: C_in * F = %d must be a multiple of 4", z.Ci * F);
+    prm.seg[i].U = z.U;
+    prm.seg[i].X = z.X;
+    prm.seg[i].Ci = z.Ci;
+    prm.seg[i].ncomp = z.ncomp;
+    prm.seg[i].cplus = z.cplus;
+    prm.seg[i].cminus = z.cminus;
+    prm.seg[i].n_stage = z.Ci * F / 4;
+    prm.seg[i].pad = 0;
+    S += prm.seg[i].n_stage;
+  }
+  prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  prm.sx = sx;
+  prm.out = out;
+  prm.E = E;
+  prm.out_es = out_edge_stride;
+  prm.comp_off[0] = comp_off0;
+  prm.comp_off[1] = comp_off1;
+  prm.n_mt = (int)ceil_div(E, SE3_TILE_E);
+  prm.n_nt = Co / N;
+  prm.S = S;
+  prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages : z_env_int("SE3B200_Z_FLUSH", 8));
+  const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
+  cudaStream_t s = as_stream(stream);
+  if (mode == 2) return csz == 1 ? launch_z<2, 128, 1>(prm, s) : launch_z<2, 128, 2>(prm, s);
+  if (N == 256) return csz == 1 ? launch_z<1, 256, 1>(prm, s) : launch_z<1, 256, 2>(prm, s);
+  return csz == 1 ? launch_z<1, 128, 1>(prm, s) : launch_z<1, 128, 2>(prm, s);
+}

@@ -289,6 +289,10 @@ class ConvSE3(nn.Module):
             # the edge-aligned images serve a ConvSE3 only if EVERY pair has a plan (all launches of an output degree then
             # accumulate in the aligned frame); otherwise keep the global-frame images of 4.2-4.3 for the covered pairs
             aligned_images = use_aligned() and len(bases) == len(self.pairs)
+            zplan = None
+            if aligned_images and use_zgemm() and self.zgemm_eligible({pair: 16 * ((rv[0] + 1 + 15) // 16) for pair, rv in bases.items()}):
+                zplan = {}                    # (do, m) -> dict(img, degs): one GEMM per output degree and |m|
+                fps = {}
             for (di, do), (r, V) in bases.items():
                 pc = self.kernel_unary[f'({di},{do})']
                 lin = pc.rp.net['6']
@@ -298,7 +302,18 @@ class ConvSE3(nn.Module):
                 Fp[:, r] = lin.bias
                 Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
                 Vp[:, :r] = V.float()
-                if aligned_images:
+                if zplan is not None:
+                    # the aligned weights w0, (a_m, b_m) = constant combinations of the F frequencies (rows (o,i,f) of F'); they are
+                    # concatenated over the input degrees into one GEMM image per (do, m) below
+                    Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp).double()
+                    c0, ca, cb = (t.to(dev) for t in _aligned.aligned_coeffs(di, do))
+                    fps[(di, do, 0)] = torch.einsum('oifk,f->oik', Fv, c0).reshape(-1, Kp).float().contiguous()
+                    for m in range(1, min(di, do) + 1):
+                        ab = torch.stack([torch.einsum('oifk,f->oik', Fv, ca[m - 1]), torch.einsum('oifk,f->oik', Fv, cb[m - 1])], dim=2)
+                        fps[(di, do, m)] = ab.reshape(-1, Kp).float().contiguous()
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=None, al_imgs=None, z=True)
+                    del Fv
+                elif aligned_images:
                     # edge-aligned formulation: images of the weights a_m, b_m = constant combinations of the
                     # F frequencies (rows (o,i,f) of F'), one image per m
                     Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp).double()
@@ -320,9 +335,33 @@ class ConvSE3(nn.Module):
                     img = ops.pack_lowrank(Fp, pc.nc_out, pc.nc_in, pc.num_freq, Kp)
                     pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=img, imgs_f=[img] if pc.num_freq == 1 else None)
                 del Fp
-        plan = dict(D=D, pairs=pairs)
+            if zplan is not None:
+                for do, mo in self.fiber_out:
+                    for m in range(do + 1):
+                        degs = [(di, mi) for di, mi in self.fiber_in if di >= m]
+                        if not degs:
+                            continue
+                        img, S = ops.zgemm_image([(fps.pop((di, do, m)), mi) for di, mi in degs], mo, 1 if m == 0 else 2)
+                        zplan[(do, m)] = dict(img=img, S=S, degs=degs)
+                del fps
+        plan = dict(D=D, pairs=pairs, z=zplan)
         pk['lr'] = plan
         return plan
+
+    def zgemm_eligible(self, kps):
+        """Shapes the one-GEMM kernel takes: every C_out a multiple of 128, every C_in a multiple of 4 (one stage = 64 K values),
+        at most 16 K segments per launch (a pair with K = 16 j contributes j), and |g|_2 small enough for the fp16 operands
+        (|Z| <= 2^10 |U|, |U_k| <= |g|_2 <= 11.32 (max|ln.w| + max|ln.b|))."""
+        if any(mo % 128 for _, mo in self.fiber_out) or any(mi % 4 for _, mi in self.fiber_in):
+            return False
+        for do, _ in self.fiber_out:
+            if sum(kps[(di, do)] // 16 for di, _ in self.fiber_in) > 16:
+                return False
+        for di, do in self.pairs:
+            ln = self.kernel_unary[f'({di},{do})'].rp.net['4']
+            if 11.32 * (float(ln.weight.abs().max()) + float(ln.bias.abs().max())) > 60.0:
+                return False
+        return True
 
     def pack_weights(self, free_master=False, max_distance=None):
         """Build the tensor-core weight images now.  With max_distance (an upper bound on the neighbour distances the model
@@ -366,6 +405,11 @@ def input_side(di, do):
     return di < do and di <= 1 and not os.environ.get('SE3B200_NO_INPUT_SIDE')
 
 
+def use_zgemm():
+    """One GEMM per (degree_out, |m|) with the A operand generated on the fly instead of the R-first kernels."""
+    return not os.environ.get('SE3B200_NO_ZGEMM')
+
+
 def use_aligned():
     """Edge-aligned evaluation of the low-rank path: 2 FMAs per radial weight instead of 2 l_out + 1."""
     return not os.environ.get('SE3B200_NO_ALIGNED')
@@ -376,11 +420,38 @@ class Geometry:
 
     def __init__(self, rel_pos, max_degree):
         self.rel_pos, self.max_degree, self._frames = rel_pos, max_degree, None
+        # run-time checks of the low-rank plans, as (ConvSE3, stats [pairs, 2]) : None = check inside every ConvSE3 (one host
+        # synchronisation each); a list = the caller collects them and checks once per forward (SE3Transformer.forward)
+        self.deferred = None
+        self._dmax = None
+
+    def d_max(self, rel_dist):
+        if self._dmax is None:
+            self._dmax = float(rel_dist.max())          # the one host synchronisation of the plan lookup, once per forward
+        return self._dmax
 
     def frames(self):
+        """Per-edge Wigner matrices D_l(R_e) (se3_frames_fwd, float64 arithmetic on the device; SE3B200_HOST_FRAMES=1: the
+        float64 torch restatement in aligned.py)."""
         if self._frames is None:
-            self._frames = _aligned.EdgeFrames(self.rel_pos, self.max_degree)
+            if os.environ.get('SE3B200_HOST_FRAMES'):
+                self._frames = _aligned.EdgeFrames(self.rel_pos, self.max_degree)
+            else:
+                self._frames = _aligned.EdgeFrames(self.rel_pos, self.max_degree, D=ops.frames(self.rel_pos, self.max_degree))
         return self._frames
+
+
+def check_lowrank_stats(checks):
+    """checks: [(ConvSE3, stats [pairs, 2] = (max |g - U V^T|, max |g|) of one forward)].  ONE host synchronisation for all of
+    them; returns the ConvSE3 modules whose cached radial basis does not cover this forward's distances."""
+    if not checks:
+        return []
+    worst = torch.stack([torch.where(have, st[:, 0] / st[:, 1].clamp(min=1e-30), torch.zeros_like(st[:, 0])).max() for _, st, have in checks]).cpu()
+    return [conv for (conv, _, _), w in zip(checks, worst.tolist()) if not (w <= conv.LR_RUNTIME_TOL)]
+
+
+class LowRankPlanMiss(RuntimeError):
+    """The radial trunk outputs of a forward left the cached low-rank subspace (distances beyond the plan's range)."""
 
 
 def conv_forward(convs, inp, edge_info, rel_dist, basis):
@@ -399,62 +470,110 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
     n_tiles = (E + ops.TILE_E - 1) // ops.TILE_E
 
     states = []
+    capturing = torch.cuda.is_current_stream_capturing()
     for conv in convs:
         assert conv.pairs == c0.pairs and conv.in_dim == c0.in_dim
         pk = conv.packed()
         feat = conv.edge_features(edge_info, rel_dist)
         assert feat.shape[-1] == conv.in_dim, f'edge feature width {feat.shape[-1]} != {conv.in_dim}'
-        g = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs))
         tc_ok = {pair: conv.tc_eligible(*pair) for pair in conv.pairs}
         # low-rank radial path (distance-only radial functions): U = G V with the pair's cached basis, K = r+1 <= 64
-        lr, plan = {}, None
-        if conv.free_master and pk.get('lr') is not None and not os.environ.get('SE3B200_NO_LOWRANK'):
-            plan = pk['lr']                         # built by pack_weights(max_distance=...) before the masters went away:
+        lr, lr_plan = {}, None
+        if os.environ.get('SE3B200_NO_LOWRANK') or conv.edge_dim != 0:
+            pass
+        elif conv.free_master and pk.get('lr') is not None:
+            lr_plan = pk['lr']                      # built by pack_weights(max_distance=...) before the masters went away:
                                                     # the only image there is, whatever the edge count
-        elif conv.edge_dim == 0 and ops.lowrank_enabled(E) and not torch.cuda.is_current_stream_capturing() and any(tc_ok.values()):
-            if conv.free_master:
-                plan = pk.get('lr')
-            else:
-                plan = conv.lowrank_plan(float(rel_dist.max()))      # cached; one host sync for the distance range
-        if plan is not None and plan['pairs']:
-            # U = G V for every pair in one batched GEMM, the residual check of the cached subspace in a second one
-            if 'Vstack' not in plan:
+        elif ops.lowrank_enabled(E) and any(tc_ok.values()) and not conv.free_master and not getattr(conv, '_lr_blocked', False):
+            if capturing:
+                lr_plan = pk.get('lr')              # built by the warm-up forwards; the residual check below still covers it
+            else:                                   # cached; needs the distance range (one host sync per forward, in Geometry)
+                lr_plan = conv.lowrank_plan(geom.d_max(rel_dist) if geom is not None else float(rel_dist.max()))
+        g, U, zplan = None, None, None
+        if lr_plan is not None and lr_plan['pairs']:
+            if 'Vstack' not in lr_plan:
                 Vs = torch.zeros((len(conv.pairs), ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
-                ones_col = torch.zeros(len(conv.pairs), dtype=torch.long, device=dev)
+                ones_col = torch.zeros(len(conv.pairs), dtype=torch.int32, device=dev)
                 have = torch.zeros(len(conv.pairs), dtype=torch.bool, device=dev)
                 for pi, pair in enumerate(conv.pairs):
-                    pp = plan['pairs'].get(pair)
+                    pp = lr_plan['pairs'].get(pair)
                     if pp is not None:
                         Vs[pi] = pp['V']
                         ones_col[pi] = pp['r']
                         have[pi] = True
-                plan['Vstack'], plan['ones_col'], plan['have'] = Vs, ones_col, have
-            Vs = plan['Vstack']
-            U = torch.bmm(g, Vs)                                           # [pairs, E, 64]
-            resid = (g - torch.bmm(U, Vs.transpose(1, 2))).abs().amax(dim=(1, 2)) / g.abs().amax(dim=(1, 2)).clamp(min=1e-30)
-            worst = torch.where(plan['have'], resid, torch.zeros_like(resid)).max()
-            U[torch.arange(len(conv.pairs), device=dev), :, plan['ones_col']] = 1.0
+                lr_plan['Vstack'], lr_plan['ones_col'], lr_plan['have'] = Vs, ones_col, have
+            # trunk + U = G V + the residual statistics of the cached subspace on THIS forward's edges, one kernel
+            covered = len(lr_plan['pairs']) == len(conv.pairs)
+            stats = torch.zeros((len(conv.pairs), 2), dtype=torch.float32, device=dev)
+            U, g = ops.radial_trunk_u(feat, pk['trunk'], lr_plan['Vstack'], lr_plan['ones_col'], stats, want_g=not covered)
             for pi, pair in enumerate(conv.pairs):
-                pp = plan['pairs'].get(pair)
+                pp = lr_plan['pairs'].get(pair)
                 if pp is not None:
                     lr[pair] = dict(Kp=pp['Kp'], U=U[pi], img=pp['img'], imgs_f=pp.get('imgs_f'), al_imgs=pp.get('al_imgs'))
-            if float(worst) > conv.LR_RUNTIME_TOL:
+            check = (conv, stats, lr_plan['have'])
+            if geom is not None and geom.deferred is not None:
+                geom.deferred.append(check)          # checked once per forward by the caller
+            elif check_lowrank_stats([check]):
                 # the fp32 trunk outputs of this forward leave the cached subspace (distances beyond the plan's range)
                 if conv.free_master:
-                    raise RuntimeError(f'low-rank radial plan does not cover this input (residual {float(worst):.1e}); '
-                                       'pack_weights(max_distance=...) was given too small a distance')
+                    raise LowRankPlanMiss('low-rank radial plan does not cover this input; pack_weights(max_distance=...) was given too '
+                                          'small a distance')
                 lr = {}                              # evaluate this ConvSE3 with the direct K = 128 kernel
+            if lr and covered and geom is not None:
+                zplan = lr_plan.get('z')
         outs = {do: torch.empty((E, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
-        al = geom is not None and len(lr) == len(conv.pairs) and all(v.get('al_imgs') is not None for v in lr.values())
-        if not al and any(v.get('img') is None and v.get('imgs_f') is None for v in lr.values()):
-            # the plan holds edge-aligned images only (DESIGN.md 4.4); they need the per-forward Geometry
+        al = zplan is None and geom is not None and len(lr) == len(conv.pairs) and all(v.get('al_imgs') is not None for v in lr.values())
+        if zplan is None and not al and any(v.get('img') is None and v.get('imgs_f') is None for v in lr.values()):
+            # the plan holds edge-aligned images only (DESIGN.md 4.4-4.5); they need the per-forward Geometry
             if geom is None:
                 raise RuntimeError('ConvSE3 was called with a (flat, plan) basis: the edge-aligned low-rank plan needs the third element, '
                                    'model.Geometry(rel_pos, max_degree), as SE3Transformer.forward passes it (or set SE3B200_NO_ALIGNED=1)')
             lr = {}                                  # mixed eligibility inside one ConvSE3: direct kernels for this forward
-        states.append(dict(conv=conv, pk=pk, g=g, outs=outs, use_tc=tc_ok, lr=lr, aligned=al))
+        if zplan is None and len(lr) < len(conv.pairs) and g is None:
+            g = ops.radial_trunk(feat, pk['trunk'], len(conv.pairs))       # the direct kernels consume g itself
+        states.append(dict(conv=conv, pk=pk, g=g, U=U, outs=outs, use_tc=tc_ok, lr=lr, aligned=al, z=zplan, lr_plan=lr_plan))
+    states_z_and_rest = list(states)            # in the order of `convs`
+    z_states = [st for st in states if st['z'] is not None]
+    states = [st for st in states if st['z'] is None]
+    if z_states:
+        # ---- production path: neighbour features rotated into the edge frame once per input degree, then ONE
+        # tensor-core GEMM per (conv, degree_out, |m|) over all input degrees, then the rotation back to the global frame
+        frames = geom.frames()
+        sx = ops.edge_scale(inp, idx, max(di for di, _ in c0.fiber_in))
+        per_tile = sum(mi * to_order(di) for di, mi in c0.fiber_in) * ops.TILE_E * 4
+        tpc = max(1, min(n_tiles, T_WORKSPACE_BYTES // per_tile))
+        for t0 in range(0, n_tiles, tpc):
+            tc = min(tpc, n_tiles - t0)
+            e0 = t0 * ops.TILE_E
+            ec = min(E - e0, tc * ops.TILE_E)
+            X = {di: ops.rotgather(inp[str(di)], idx, frames.D[di] if di > 0 else None, t0, tc) for di, _ in c0.fiber_in}
+            for st in z_states:
+                conv = st['conv']
+                for do, mo in conv.fiber_out:
+                    P = to_order(do)
+                    full = all((do, m) in st['z'] for m in range(do + 1))
+                    if do == 0:
+                        Op = st['outs'][0][e0:e0 + ec]                   # [ec, mo, 1] is [ec, 1, mo]
+                    else:
+                        Op = (torch.empty if full else torch.zeros)((ec, P, mo), dtype=torch.float32, device=dev)
+                    for m in range(do + 1):
+                        zp = st['z'].get((do, m))
+                        if zp is None:
+                            continue
+                        segs, alg = [], 0
+                        for di, mi in zp['degs']:
+                            pi = conv.pairs.index((di, do))
+                            for kc in range(st['lr'][(di, do)]['Kp'] // 16):
+                                segs.append((st['U'][pi, e0:e0 + ec, 16 * kc:], X[di], mi, to_order(di), di + m, di - m))
+                            alg += ec * mo * mi * 2 * (ops.RADIAL_MID + P) * (1 if m == 0 else 2)
+                        ops.zgemm(segs, zp['img'], sx[e0:e0 + ec], ec, mo, 1 if m == 0 else 2, Op, P * mo, [(do + m) * mo, (do - m) * mo],
+                                  alg_flops=alg, tag=f'lo{do}m{m}Co{mo}S{zp["S"]}')
+                    if do > 0:                          # back to the global frame: out = D_lo out'
+                        ops.fold_basis(Op.view(1, ec, P, mo), frames.D[do][e0:e0 + ec].reshape(-1), ec, mo, P, P, 1,
+                                       st['outs'][do][e0:e0 + ec], accumulate=False, component_major=True, name='rotate_back')
+            del X
     aligned_states = [st for st in states if st['aligned']]
-    states_all, states = states, [st for st in states if not st['aligned']]
+    states_all, states = states_z_and_rest, [st for st in states if not st['aligned']]
 
     # chunk over edge tiles so that the largest T block fits the workspace
     worst = max(ops.t_numel(1, mi, to_order(min(di, do)), to_order(do)) * 4
@@ -808,6 +927,33 @@ class SE3Transformer(nn.Module):
     @torch.no_grad()
     def forward(self, feats, coors, mask=None, adj_mat=None, edges=None, return_type=None, return_pooled=False,
                 neighbor_mask=None, global_feats=None):
+        kw = dict(mask=mask, adj_mat=adj_mat, edges=edges, return_type=return_type, return_pooled=return_pooled,
+                  neighbor_mask=neighbor_mask, global_feats=global_feats)
+        out, checks = self._forward_once(feats, coors, **kw)
+        if torch.cuda.is_current_stream_capturing():
+            self._graph_checks = checks               # static tensors of the graph: GraphedForward reads them after each replay
+            return out
+        bad = check_lowrank_stats(checks)             # the one host synchronisation of the low-rank plans, once per forward
+        if bad:
+            self.handle_plan_miss(bad)
+            out, checks = self._forward_once(feats, coors, **kw)
+            assert not check_lowrank_stats(checks)
+        return out
+
+    @staticmethod
+    def handle_plan_miss(bad):
+        """The radial trunk outputs of a forward left the cached low-rank subspace of these ConvSE3 (distances beyond the plan's
+        range): with released masters there is nothing to fall back to; otherwise they run on the direct kernels from now on."""
+        if any(conv.free_master for conv in bad):
+            raise LowRankPlanMiss('low-rank radial plan does not cover this input; pack_weights(max_distance=...) was given too small a distance')
+        import warnings
+        warnings.warn(f'{len(bad)} ConvSE3 left their low-rank radial plan (residual above {ConvSE3.LR_RUNTIME_TOL:g}): evaluating them with '
+                      'the direct K = 128 kernels')
+        for conv in bad:
+            conv._lr_blocked = True
+
+    def _forward_once(self, feats, coors, mask=None, adj_mat=None, edges=None, return_type=None, return_pooled=False,
+                      neighbor_mask=None, global_feats=None):
         assert not (self.accept_global_feats ^ exists(global_feats)), 'you cannot pass in global features unless you init the class correctly'
         _mask = mask
         # float64 models / inputs (reference tests/test_equivariance.py:228-258 runs under a float64 default dtype): the kernels
@@ -903,7 +1049,9 @@ class SE3Transformer(nn.Module):
             a = self.adj_emb(adj_indices.gather(2, idx))
             e = torch.cat((e, a), dim=-1) if exists(e) else a
 
-        basis = ops.basis_flat(rel_pos, self.num_degrees - 1) + (Geometry(rel_pos, self.num_degrees - 1),)
+        geom = Geometry(rel_pos, self.num_degrees - 1)
+        geom.deferred = []
+        basis = ops.basis_flat(rel_pos, self.num_degrees - 1) + (geom,)
         edge_info = (idx, nmask, e)
         x = self.conv_in(feats, edge_info, rel_dist=rel_dist, basis=basis)
         for conv, nonlin in self.convs:
@@ -923,8 +1071,8 @@ class SE3Transformer(nn.Module):
         if exists(out_dtype):
             x = {k: v.to(out_dtype) for k, v in x.items()}
         if exists(return_type):
-            return x[str(return_type)]
-        return x
+            return x[str(return_type)], geom.deferred
+        return x, geom.deferred
 
 
 class GraphedForward:
@@ -951,15 +1099,27 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = model(self.feats, self.coors, self.mask, **self.static_kw)
+        self.checks = model._graph_checks
 
-    def __call__(self, feats, coors, mask=None):
+    def __call__(self, feats, coors, mask=None, **tensor_kwargs):
         if isinstance(feats, dict):
             for k, v in feats.items():
                 self.feats[k].copy_(v, non_blocking=True)
         else:
             self.feats.copy_(feats, non_blocking=True)
         self.coors.copy_(coors, non_blocking=True)
+        if (mask is None) != (self.mask is None):
+            raise ValueError('GraphedForward: `mask` must be given exactly when the graph was captured with one')
         if mask is not None:
             self.mask.copy_(mask, non_blocking=True)
+        for k, v in tensor_kwargs.items():                # edges / adj_mat / global_feats captured as static buffers
+            if not torch.is_tensor(self.static_kw.get(k)):
+                raise ValueError(f'GraphedForward: {k} was not a tensor argument of the captured forward')
+            self.static_kw[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        # the run-time check of the low-rank plans, read once per replay (the tensors are static outputs of the graph)
+        bad = check_lowrank_stats(self.checks)
+        if bad:
+            raise LowRankPlanMiss('captured forward: the low-rank radial plan does not cover this input (distances beyond the range '
+                                  'seen when the graph was captured); build a new graph or pack_weights(max_distance=...) for a larger range')
         return self.out

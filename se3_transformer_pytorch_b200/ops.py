@@ -40,6 +40,15 @@ _SIGNATURES = {
     'se3_fold_basis_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_fold_basis_cm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_rotate_back_fwd': (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_void_p, c_void_p]),
+    'se3_radial_trunk_u_fwd': (c_int, [c_void_p, c_int64, c_int, c_int] + [c_void_p] * 7),
+    'se3_frames_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5),
+    'se3_rotgather_fwd': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_int64, c_int64, c_void_p, c_void_p]),
+    'se3_rowabsmax_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    'se3_edge_scale_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_zgemm_tile_n': (c_int, [c_int, c_int]),
+    'se3_zgemm_image_bytes': (c_int64, [c_int, c_int, c_int]),
+    'se3_zgemm_pack': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_zgemm_fwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
@@ -347,13 +356,13 @@ def tbuild_blocks(x, idx, blocks, P, F, tile_begin=0, tile_count=None, out=None)
     return out
 
 
-def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False):
+def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False, name='fold_basis'):
     """out [E,Co,P] (+)= sum_{f,q} basis_pair[e,p,q,f] S[f,e,o,q]; S [F,E,Co,Q] (or [F,E,Q,Co] if component_major),
     basis_pair the [E,P,Q,F] rows of these edges."""
     _require_cuda(S, basis_pair, out)
     assert S.is_contiguous() and basis_pair.is_contiguous() and out.is_contiguous()
     nbytes = 4 * (S.numel() + basis_pair.numel() + out.numel() * (2 if accumulate else 1))
-    with torch.cuda.device(out.device), _timed('fold_basis', flops=2 * E * Co * P * Q * F, nbytes=nbytes):
+    with torch.cuda.device(out.device), _timed(name, flops=2 * E * Co * P * Q * F, nbytes=nbytes):
         fn = lib().se3_fold_basis_cm_fwd if component_major else lib().se3_fold_basis_fwd
         _check(fn(_p(S), _p(basis_pair), E, Co, P, Q, F, int(accumulate), _p(out), _stream()))
 
@@ -436,6 +445,143 @@ def pairwise_lr(U, w_img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, o
             offs = (ctypes.c_int * P)(*p_off)
             _check(lib().se3_pairwise_lr_strided_fwd(_p(U), _p(w_img), _p(T), E, Co, Ci, F, P, Kp, int(accumulate), _p(out),
                                                      out_strides[0], out_strides[1], offs, _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# production path: low-rank radial basis + edge-aligned frames as one GEMM per (degree_out, |m|)  (csrc/zgemm.cu, aligned.cu)
+# ---------------------------------------------------------------------------------------------------------
+class ZSeg(ctypes.Structure):
+    _fields_ = [('U', c_void_p), ('X', c_void_p), ('Ci', c_int), ('ncomp', c_int), ('cplus', c_int), ('cminus', c_int)]
+
+
+def radial_trunk_u(feat, params, V, ones_col, stats, want_g=False):
+    """Trunk + radial coordinates: feat [E,in_dim], params [pairs, stride], V [pairs,128,64] fp32, ones_col [pairs] int32,
+    stats [pairs,2] fp32 (accumulates (max residual, max |g|)) -> U [pairs,E,64] (, g [pairs,E,128])."""
+    _require_cuda(feat, params, V, ones_col, stats)
+    feat = _f32(feat)
+    E, in_dim = feat.shape
+    num_pairs = params.shape[0]
+    assert V.shape == (num_pairs, RADIAL_MID, 64) and V.is_contiguous() and ones_col.dtype == torch.int32 and stats.is_contiguous()
+    U = torch.empty((num_pairs, E, 64), dtype=torch.float32, device=feat.device)
+    g = torch.empty((num_pairs, E, RADIAL_MID), dtype=torch.float32, device=feat.device) if want_g else None
+    flops = 2 * E * num_pairs * RADIAL_MID * (in_dim + RADIAL_MID + 2 * 64)
+    with torch.cuda.device(feat.device), _timed('radial_trunk', flops=flops, nbytes=4 * (feat.numel() + params.numel() + V.numel() + U.numel())):
+        _check(lib().se3_radial_trunk_u_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(V), _p(ones_col), _p(g), _p(U), _p(stats), _stream()))
+    return U, g
+
+
+_FRAME_TABLES = {}
+
+
+def _frame_tables(lmax, device):
+    key = (lmax, str(device))
+    if key not in _FRAME_TABLES:
+        from . import aligned
+        xs_t, pin_t, keep = [None], [None], []
+        ns = [0]
+        for l in range(1, lmax + 1):
+            xs, pin = aligned._samples(l, device)
+            xs, pin = xs.contiguous(), pin.contiguous()
+            keep += [xs, pin]
+            xs_t.append(xs.data_ptr()); pin_t.append(pin.data_ptr()); ns.append(xs.shape[0])
+        mk = lambda vals: (c_void_p * (lmax + 1))(*[c_void_p(v) if v else None for v in vals])
+        _FRAME_TABLES[key] = (mk(xs_t), mk(pin_t), (c_int * (lmax + 1))(*ns), keep)
+    return _FRAME_TABLES[key]
+
+
+def frames(rel_pos, lmax):
+    """Wigner matrices of the edge frames: rel_pos [...,3] -> [None, D_1 [E,3,3], ..., D_lmax] fp32 (float64 arithmetic inside)."""
+    _require_cuda(rel_pos)
+    rel_pos = _f32(rel_pos).reshape(-1, 3)
+    E = rel_pos.shape[0]
+    D = [None] + [torch.empty((E, 2 * l + 1, 2 * l + 1), dtype=torch.float32, device=rel_pos.device) for l in range(1, lmax + 1)]
+    if lmax >= 1:
+        xs, pin, ns, _ = _frame_tables(lmax, rel_pos.device)
+        dptr = (c_void_p * (lmax + 1))(*[c_void_p(t.data_ptr()) if t is not None else None for t in D])
+        with torch.cuda.device(rel_pos.device), _timed('frames', nbytes=E * (12 + 4 * sum((2 * l + 1) ** 2 for l in range(1, lmax + 1)))):
+            _check(lib().se3_frames_fwd(_p(rel_pos), E, lmax, xs, pin, ns, dptr, _stream()))
+    return D
+
+
+def rotgather(x, idx, D, tile_begin=0, tile_count=None, out=None):
+    """x [b,n,Ci,Q], idx [b,n,k], D [E,Q,Q] (None for Q = 1) -> X [tile_count, Ci, Q, 128]: rotated neighbour features."""
+    _require_cuda(x, idx, D)
+    x = _f32(x)
+    b, n, Ci, Q = x.shape
+    k = idx.shape[-1]
+    E = b * n * k
+    n_tiles = (E + TILE_E - 1) // TILE_E
+    if tile_count is None:
+        tile_count = n_tiles - tile_begin
+    numel = tile_count * Ci * Q * TILE_E
+    if out is None or out.numel() < numel:
+        out = torch.empty(numel, dtype=torch.float32, device=x.device)
+    Ec = min(E - tile_begin * TILE_E, tile_count * TILE_E)
+    nbytes = 4 * Ec * (2 * Ci * Q + (Q * Q if Q > 1 else 0)) + 8 * Ec
+    with torch.cuda.device(x.device), _timed('rotgather', flops=2 * Ec * Ci * Q * Q, nbytes=nbytes):
+        _check(lib().se3_rotgather_fwd(_p(x), _p(idx.contiguous()), _p(D), b, n, k, Ci, Q, tile_begin, tile_count, _p(out), _stream()))
+    return out
+
+
+def edge_scale(feats, idx, max_degree):
+    """Power-of-two scale per edge from the largest |component| of the neighbour's features (all degrees): [E] fp32."""
+    b, n, k = idx.shape
+    first = True
+    nodemax = torch.empty(b * n, dtype=torch.float32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        for t in feats.values():
+            t = _f32(t)
+            _check(lib().se3_rowabsmax_fwd(_p(t), b * n, t.shape[2] * t.shape[3], int(not first), _p(nodemax), _stream()))
+            first = False
+        sx = torch.empty(b * n * k, dtype=torch.float32, device=idx.device)
+        _check(lib().se3_edge_scale_fwd(_p(nodemax), _p(idx.contiguous()), b, n, k, max_degree, _p(sx), _stream()))
+    return sx
+
+
+def zgemm_tile_n(Co, mode):
+    return lib().se3_zgemm_tile_n(Co, mode)
+
+
+def zgemm_image(parts, Co, mode):
+    """parts: [(Fp [Co*Ci*F, Kp] fp32, Ci)] in K order (one entry per input degree; Kp / 16 sub-segments each, F = mode) ->
+    (uint8 image, total_stages)."""
+    F = mode
+    stages = [(Fp.shape[1] // 16) * (Ci * F // 4) for Fp, Ci in parts]
+    S = sum(stages)
+    nbytes = lib().se3_zgemm_image_bytes(Co, mode, S)
+    if nbytes < 0:
+        raise RuntimeError(f'zgemm_image: unsupported shape Co={Co} mode={mode}')
+    dev = parts[0][0].device
+    img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s0 = 0
+    with torch.cuda.device(dev):
+        for Fp, Ci in parts:
+            _require_cuda(Fp)
+            Fp = _f32(Fp)
+            Kp = Fp.shape[1]
+            assert Fp.shape[0] == Co * Ci * F and Kp % 16 == 0 and (Ci * F) % 4 == 0
+            for kc in range(Kp // 16):
+                _check(lib().se3_zgemm_pack(_p(Fp), Kp, 16 * kc, Co, Ci * F, mode, S, s0, _p(img), _stream()))
+                s0 += Ci * F // 4
+    return img, S
+
+
+def zgemm(segs, w_img, sx, E, Co, mode, out, out_edge_stride, comp_off, flush_stages=0, alg_flops=0, tag=''):
+    """segs: [(U [E,64] view (row stride 64; column offset folded into the pointer), X buffer, Ci, ncomp, cplus, cminus)]."""
+    _require_cuda(w_img, sx, out)
+    arr = (ZSeg * len(segs))()
+    Ktot = 0
+    for i, (U, X, Ci, ncomp, cplus, cminus) in enumerate(segs):
+        _require_cuda(U, X)
+        assert U.dtype == torch.float32 and U.stride(-1) == 1 and (U.dim() == 1 or U.stride(0) == 64)
+        arr[i] = ZSeg(U.data_ptr(), X.data_ptr(), Ci, ncomp, cplus, cminus)
+        Ktot += Ci * mode * 16
+    N = zgemm_tile_n(Co, mode)
+    mma = 2 * E * Co * Ktot * 3 * mode                   # issued: 3 fp16 passes; mode 2 feeds two accumulators from every B tile
+    nbytes = w_img.numel() + 4 * E * Co * mode + sum(4 * E * s[2] * (mode + 16) for s in segs)
+    with torch.cuda.device(out.device), _timed('zgemm', flops=alg_flops, nbytes=nbytes, tag=tag or f'mode{mode}N{N}K{Ktot}', mma=mma):
+        _check(lib().se3_zgemm_fwd(arr, len(segs), _p(w_img), _p(sx), E, Co, mode, _p(out), out_edge_stride, comp_off[0],
+                                   comp_off[1] if len(comp_off) > 1 else 0, flush_stages, _stream()))
 
 
 # max-abs residual of the radial basis relative to max|G|.  The fp32 trunk itself carries ~6e-7..1e-6 of rounding noise

@@ -122,6 +122,15 @@ BIG_CASES = [
 ]
 
 
+# widths the one-GEMM production kernel takes (every fiber a multiple of 128 channels), small enough for the
+# reference's materialising CPU path
+ZCASES = [
+    dict(name='z128', ctor=dict(dim=128, heads=2, dim_head=64, depth=1, num_degrees=3, output_degrees=2, num_neighbors=6, valid_radius=10),
+         b=1, n=20, no_capture=True),
+    dict(name='z256_deg4', ctor=dict(dim=256, heads=4, dim_head=64, depth=1, num_degrees=4, num_neighbors=5), b=2, n=14, no_capture=True),
+]
+
+
 def build_inputs(case):
     b, n = case['b'], case['n']
     name = case['name']
@@ -268,10 +277,10 @@ if __name__ == '__main__':
         gen_sh_basis()
     if 'rot' in which:
         gen_equivariance_inputs()
-    if 'models' in which or 'big' in which:
+    if 'models' in which or 'big' in which or 'z' in which:
         kpath = os.path.join(HERE, 'state_keys.json')
         all_keys = json.load(open(kpath)) if os.path.exists(kpath) else {}
-        for case in (CASES if 'models' in which else []) + (BIG_CASES if 'big' in which else []):
+        for case in (CASES if 'models' in which else []) + (BIG_CASES if 'big' in which else []) + (ZCASES if 'z' in which else []):
             all_keys[case['name']] = run_case(case)
         with open(kpath, 'w') as f:
             json.dump(all_keys, f, indent=0, sort_keys=True)

@@ -13,6 +13,10 @@ MODEL_CASES = ['cfg1', 'deg4', 'af2', 'edges_sparse', 'ragged', 'tc_deg2', 'tc_d
 BIG_CASES = ['cfg3', 'cfg4_b2']
 
 
+# widths the one-GEMM production kernel takes (every fiber a multiple of 128 channels)
+Z_CASES = ['z128', 'z256_deg4']
+
+
 def load_case(name):
     z = dict(np.load(os.path.join(GOLDEN, f'model_{name}.npz')))
     cfg = json.loads(str(z.pop('config')))

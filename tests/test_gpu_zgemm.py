@@ -1,0 +1,201 @@
+"""Kernel-level parity of the production path's kernels (csrc/zgemm.cu, aligned.cu, radial_trunk_u) through the C ABI against
+float64 restatements of what each computes; the whole-model / oracle comparisons at the benchmarked shape are
+in test_gpu_headline.py.  Tolerances are written next to each assert (north_star: 1e-4 relative on outputs)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _x_layout(xp):
+    """x' [E, Ci, ncomp] -> kernel layout [tiles][Ci][ncomp][128] (zero rows past E)."""
+    E, Ci, nc = xp.shape
+    tiles = (E + 127) // 128
+    buf = torch.zeros(tiles * 128, Ci, nc, dtype=torch.float32, device=xp.device)
+    buf[:E] = xp
+    return buf.reshape(tiles, 128, Ci, nc).permute(0, 2, 3, 1).contiguous().reshape(-1)
+
+
+def _zgemm_reference(mode, segs, Co):
+    """float64: segs = [(U [E,Kp], Fp [Co*Ci*F, Kp], x' [E,Ci,ncomp], cplus, cminus)] -> out [E, mode, Co]."""
+    outs = None
+    for U, Fp, xp, cp, cm in segs:
+        E, Ci = xp.shape[0], xp.shape[1]
+        Fv = Fp.double().reshape(Co, Ci, mode, -1)
+        Ud = U.double()[:, :Fv.shape[-1]]
+        w = torch.einsum('ek,oifk->eoif', Ud, Fv)                     # the radial weights of this segment
+        xd = xp.double()
+        if mode == 1:
+            o = torch.einsum('eoi,ei->eo', w[..., 0], xd[:, :, cp])[:, None]
+        else:
+            a, b = w[..., 0], w[..., 1]
+            op = torch.einsum('eoi,ei->eo', a, xd[:, :, cp]) - torch.einsum('eoi,ei->eo', b, xd[:, :, cm])
+            om = torch.einsum('eoi,ei->eo', b, xd[:, :, cp]) + torch.einsum('eoi,ei->eo', a, xd[:, :, cm])
+            o = torch.stack([op, om], dim=1)
+        outs = o if outs is None else outs + o
+    return outs
+
+
+def _run_zgemm(mode, Co, E, seg_shapes, flush=0, seed=0, x_scale=1.0, positive=False):
+    """seg_shapes: [(Ci, ncomp, cplus, cminus, Kp)].  Returns (gpu out [E, mode, Co], float64 reference)."""
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    rnd = (lambda *s: torch.rand(*s, generator=g, device=DEV) + 0.1) if positive else (lambda *s: torch.randn(*s, generator=g, device=DEV))
+    segs_ref, segs_k, parts = [], [], []
+    for Ci, nc, cp, cm, Kp in seg_shapes:
+        U = torch.zeros(E, 64, device=DEV)
+        U[:, :Kp] = rnd(E, Kp)
+        U[:, Kp - 1] = 1.0                                             # the bias slot
+        Fp = rnd(Co * Ci * mode, Kp) / (Ci * Kp) ** 0.5
+        xp = rnd(E, Ci, nc) * x_scale
+        segs_ref.append((U, Fp, xp, cp, cm))
+        X = _x_layout(xp)
+        for kc in range(Kp // 16):
+            segs_k.append((U[:, 16 * kc:], X, Ci, nc, cp, cm))
+        parts.append((Fp.contiguous(), Ci))
+    img, S = ops.zgemm_image(parts, Co, mode)
+    # per-edge power-of-two scales as the model makes them (from the row maximum), exercising the scale / unscale path
+    rowmax = torch.stack([s[2].abs().amax(dim=(1, 2)) for s in segs_ref]).amax(0)
+    sx = torch.exp2(torch.floor(9 - torch.log2(rowmax.clamp(min=1e-30)))).float()
+    out = torch.full((E, mode, Co), 7.0, device=DEV)
+    ops.zgemm(segs_k, img, sx, E, Co, mode, out, mode * Co, [0, Co], flush_stages=flush)
+    torch.cuda.synchronize()
+    return out, _zgemm_reference(mode, segs_ref, Co)
+
+
+@pytest.mark.parametrize('mode,Co,E,segs', [
+    (1, 256, 300, [(8, 1, 0, 0, 16)]),                                     # N = 256, 3 edge tiles (padding CTA in the 2-cluster)
+    (1, 128, 128, [(4, 3, 1, 1, 16), (12, 5, 2, 2, 16)]),                  # N = 128 tile, two input degrees
+    (1, 512, 257, [(16, 1, 0, 0, 16), (8, 3, 1, 1, 32), (4, 7, 3, 3, 16)]),  # a K = 32 pair (two sub-segments)
+    (2, 128, 300, [(6, 3, 2, 0, 16)]),                                     # (+m, -m) = components 2, 0 of an l = 1 input
+    (2, 256, 200, [(4, 3, 2, 0, 16), (10, 5, 3, 1, 32), (2, 7, 4, 2, 16)]),
+    (2, 512, 129, [(32, 7, 6, 0, 16)]),
+])
+def test_zgemm_matches_fp64(mode, Co, E, segs):
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.tc_supported(DEV, Co, 1):
+        pytest.skip('needs sm_100')
+    for flush in (0, 1, 3):
+        out, ref = _run_zgemm(mode, Co, E, segs, flush=flush, seed=flush)
+        err = rel_err(out.cpu().numpy(), ref.cpu().numpy())
+        assert err < 3e-6, f'flush={flush}: {err:.3e}'
+
+
+@pytest.mark.parametrize('x_scale', [1e-6, 1.0, 3e4])
+def test_zgemm_is_scale_invariant(x_scale):
+    """The per-edge power-of-two scale keeps the fp16 operands in range whatever the magnitude of the features."""
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.tc_supported(DEV, 128, 1):
+        pytest.skip('needs sm_100')
+    out, ref = _run_zgemm(2, 128, 200, [(8, 3, 2, 0, 16)], x_scale=x_scale)
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-6
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+def test_zgemm_headline_width_long_k(mode):
+    """cfg2 widths (C_in = C_out = 512, four input degrees: K = 32768 / 65536 per output) with all-positive operands, the
+    worst case for the round-toward-zero accumulation of the tensor cores: the periodic drain into fp32 registers keeps the
+    result within 1e-5 of float64 (the error without it is recorded next to it)."""
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.tc_supported(DEV, 512, 1):
+        pytest.skip('needs sm_100')
+    segs = [(512, 2 * l + 1, l + (1 if mode == 2 and l else 0), l - (1 if mode == 2 and l else 0), 16) for l in ((0, 1, 2, 3) if mode == 1 else (1, 2, 3))]
+    out, ref = _run_zgemm(mode, 512, 512, segs, flush=0, positive=True)
+    err = rel_err(out.cpu().numpy(), ref.cpu().numpy())
+    out2, _ = _run_zgemm(mode, 512, 512, segs, flush=1 << 20, positive=True)
+    err_nodrain = rel_err(out2.cpu().numpy(), ref.cpu().numpy())
+    print(f'zgemm mode {mode} long-K positive operands: rel err {err:.3e} (default drain), {err_nodrain:.3e} (never drained)')
+    import json, os
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/zgemm_accumulation.jsonl', 'a') as f:
+        f.write(json.dumps(dict(mode=mode, rel_err_default_drain=err, rel_err_never_drained=err_nodrain)) + '\n')
+    assert err < 1e-5
+
+
+def test_frames_match_float64_host_math():
+    """se3_frames_fwd vs the float64 torch restatement (aligned.EdgeFrames: Rodrigues rotation, Wigner matrices from the
+    harmonics at rotated sample points), including coincident points (r = 0), the axis itself and its antipode."""
+    from se3_transformer_pytorch_b200 import ops, aligned
+    g = torch.Generator().manual_seed(0)
+    rel = torch.randn(500, 3, generator=g)
+    rel[0] = 0.0
+    rel[1] = torch.tensor([0.0, 2.0, 0.0])
+    rel[2] = torch.tensor([0.0, -3.0, 0.0])
+    rel[3] = torch.tensor([1e-4, -1.0, 0.0])
+    rel[4] = torch.tensor([0.5, 0.0, 0.0])
+    rel = rel.to(DEV)
+    for lmax in (1, 3, 5):
+        D = ops.frames(rel, lmax)
+        ref = aligned.EdgeFrames(rel, lmax).D
+        for l in range(1, lmax + 1):
+            assert float((D[l] - ref[l]).abs().max()) < 2e-6, l
+            eye = torch.eye(2 * l + 1, device=DEV)
+            assert float((D[l] @ D[l].transpose(1, 2) - eye).abs().max()) < 1e-5          # orthogonal
+
+
+@pytest.mark.parametrize('li,Ci,b,n,k', [(0, 10, 1, 20, 7), (1, 6, 2, 30, 9), (3, 5, 1, 40, 16), (5, 3, 1, 12, 5)])
+def test_rotgather(li, Ci, b, n, k):
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(li)
+    Q = 2 * li + 1
+    x = torch.randn(b, n, Ci, Q, generator=g).to(DEV)
+    idx = torch.randint(0, n, (b, n, k), generator=g).to(DEV)
+    E = b * n * k
+    D = torch.randn(E, Q, Q, generator=g).to(DEV) if li else None
+    X = ops.rotgather(x, idx, D)
+    tiles = (E + 127) // 128
+    got = X[:tiles * Ci * Q * 128].reshape(tiles, Ci, Q, 128).permute(0, 3, 1, 2).reshape(tiles * 128, Ci, Q)
+    xg = x.reshape(b * n, Ci, Q)[(idx + (torch.arange(b, device=DEV) * n)[:, None, None]).reshape(-1)]
+    ref = xg if D is None else torch.einsum('eqn,eiq->ein', D.double(), xg.double()).float()
+    assert float((got[:E] - ref).abs().max()) < 1e-5
+    assert float(got[E:].abs().max()) == 0.0 if tiles * 128 > E else True
+
+
+def test_edge_scale():
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    b, n, k = 2, 16, 5
+    feats = {'0': torch.randn(b, n, 4, 1, generator=g).to(DEV) * 1e-3, '1': torch.randn(b, n, 4, 3, generator=g).to(DEV) * 50}
+    feats['1'][0, 3] = 0.0
+    feats['0'][0, 3] = 0.0
+    idx = torch.randint(0, n, (b, n, k), generator=g).to(DEV)
+    sx = ops.edge_scale(feats, idx, 1)
+    nodemax = torch.maximum(feats['0'].abs().amax(dim=(2, 3)), feats['1'].abs().amax(dim=(2, 3))).reshape(-1)
+    nm = nodemax[(idx + (torch.arange(b, device=DEV) * n)[:, None, None]).reshape(-1)]
+    v = nm * 3 ** 0.5 * sx
+    assert bool(((v < 1024) & (v >= 512))[nm > 0].all())
+    assert bool((sx[nm == 0] == 1).all())
+    assert bool((torch.log2(sx) == torch.log2(sx).round()).all())
+
+
+def test_radial_trunk_u():
+    """Fused trunk + radial coordinates: g identical to se3_radial_trunk_fwd, U = g V (ones column at r), residual statistics."""
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    E, in_dim, pairs = 200, 1, 3
+    feat = (torch.rand(E, in_dim, generator=g) * 3).to(DEV)
+    stride = ops.trunk_param_stride(in_dim)
+    params = (torch.randn(pairs, stride, generator=g) * 0.3).to(DEV)
+    g_ref = ops.radial_trunk(feat, params, pairs)
+    r = [15, 31, 20]
+    V = torch.zeros(pairs, 128, 64, device=DEV)
+    for p in range(pairs):
+        q, _ = torch.linalg.qr(torch.randn(128, r[p], generator=g))
+        V[p, :, :r[p]] = q.to(DEV)
+    ones_col = torch.tensor(r, dtype=torch.int32, device=DEV)
+    stats = torch.zeros(pairs, 2, device=DEV)
+    U, g_out = ops.radial_trunk_u(feat, params, V, ones_col, stats, want_g=True)
+    assert torch.equal(g_out, g_ref)
+    for p in range(pairs):
+        ref = g_ref[p].double() @ V[p].double()
+        assert float((U[p, :, :r[p]] - ref[:, :r[p]]).abs().max()) < 1e-5
+        assert bool((U[p, :, r[p]] == 1).all()) and float(U[p, :, r[p] + 1:].abs().max()) == 0.0
+        resid = (g_ref[p].double() - ref @ V[p].double().t()).abs().max()
+        assert abs(float(stats[p, 0]) - float(resid)) < 1e-5 * max(1.0, float(resid))
+        assert abs(float(stats[p, 1]) - float(g_ref[p].abs().max())) < 1e-6
+    U2, none = ops.radial_trunk_u(feat, params, V, ones_col, stats)
+    assert none is None and torch.equal(U2, U)

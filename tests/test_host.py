@@ -6,12 +6,12 @@ import re
 import pytest
 import torch
 
-from helpers import MODEL_CASES, BIG_CASES, load_case, state_keys
+from helpers import MODEL_CASES, BIG_CASES, Z_CASES, load_case, state_keys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('name', MODEL_CASES + BIG_CASES)
+@pytest.mark.parametrize('name', MODEL_CASES + BIG_CASES + Z_CASES)
 def test_state_dict_layout_matches_reference(name):
     """Same parameter names and shapes as the reference: load_state_dict interchange."""
     from se3_transformer_pytorch_b200 import SE3Transformer
@@ -140,10 +140,11 @@ def test_lowrank_plan_image_selection(monkeypatch):
     assert conv2.lowrank_plan(3.0) is plan2                          # cached while the distance range is covered
 
 
-@pytest.mark.parametrize('frame', ['aligned', 'global'])
+@pytest.mark.parametrize('frame', ['zgemm', 'aligned', 'global'])
 def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
-    """conv_forward's low-rank dispatch -- edge-aligned and global frame with input-side contraction
-    (4.2-4.3) (plan images, per-(l_in, m) tiles, (+m,-m) buffers, rotate-back, edge chunking)
+    """conv_forward's low-rank dispatch -- the one-GEMM production path (rotated gather, K segments per input
+    degree and 16-column block of U, component planes, rotate-back), the R-first edge-aligned path (4.4) and the global frame
+    with input-side contraction (4.2-4.3) (plan images, per-(l_in, m) tiles, (+m,-m) buffers, rotate-back, edge chunking)
     with every CUDA op replaced by a float64 torch emulation of its contract, against the reference order of operations
     (kernel = R . B first, S:336-343, with the oracle's basis).  Host logic only: the CUDA kernels have their own GPU tests."""
     import numpy as np
@@ -152,23 +153,72 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
     from se3_transformer_pytorch_b200 import ops, model as M
 
     torch.manual_seed(0)
-    b, n, k, C = 1, 40, 8, 32
+    b, n, k, C = 1, 40, 8, (128 if frame == 'zgemm' else 32)      # the one-GEMM kernel takes C_out % 128 == 0
     L = 2
     fin, fout = M.Fiber([(d, C) for d in range(L + 1)]), M.Fiber([(d, C) for d in range(L + 1)])
-    if frame == 'aligned':
+    if frame in ('aligned', 'zgemm'):
         monkeypatch.delenv('SE3B200_NO_ALIGNED', raising=False)
     else:
         monkeypatch.setenv('SE3B200_NO_ALIGNED', '1')
+    monkeypatch.delenv('SE3B200_NO_ZGEMM', raising=False)
+    monkeypatch.setenv('SE3B200_HOST_FRAMES', '1')               # float64 torch frames (the device kernel has its own GPU test)
     monkeypatch.setattr(M.ConvSE3, 'tc_eligible', lambda self, di, do: True)
     monkeypatch.setattr(ops, 'lowrank_enabled', lambda E: True)
     monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
-    monkeypatch.setattr(M, 'T_WORKSPACE_BYTES', ops.t_numel(1, C, 2, 2) * 4)       # one edge tile per chunk -> 3 chunks
+    monkeypatch.setattr(M, 'T_WORKSPACE_BYTES', ops.t_numel(1, C, 2, 2) * 4 if frame != 'zgemm' else 9 * C * ops.TILE_E * 4)  # one edge tile per chunk -> 3 chunks
     monkeypatch.setattr(ops, 'pack_lowrank', lambda Fp, Co, Ci, F, Kp: Fp.double().clone())  # "image" = F' itself
 
     conv = M.ConvSE3(fin, fout, edge_dim=0, pool=False, self_interaction=False)
 
     def radial_trunk(feat, params, num_pairs):
         return torch.stack([conv.kernel_unary[f'({di},{do})'].rp.trunk64(feat.double()) for di, do in conv.pairs]).float()
+
+    def radial_trunk_u(feat, params, V, ones_col, stats, want_g=False):
+        g = radial_trunk(feat, params, len(conv.pairs)).double()
+        U = torch.bmm(g, V.double())
+        resid = (g - torch.bmm(U, V.double().transpose(1, 2))).abs().amax(dim=(1, 2))
+        stats[:, 0] = torch.maximum(stats[:, 0], resid.float())
+        stats[:, 1] = torch.maximum(stats[:, 1], g.abs().amax(dim=(1, 2)).float())
+        U[torch.arange(len(conv.pairs)), :, ones_col.long()] = 1.0
+        return U.float(), (g.float() if want_g else None)
+
+    def rotgather(x, idx, D, tile_begin=0, tile_count=None, out=None):
+        E = idx.numel()
+        e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
+        xj = gather_rows(x, idx, e0, e1)
+        return xj if D is None else torch.einsum('eqn,eiq->ein', D[e0:e1].double(), xj)      # x'[n] = sum_q D[q,n] x[q]
+
+    def edge_scale(feats, idx, max_degree):
+        return torch.full((idx.numel(),), 4.0)
+
+    def zgemm_image(parts, Co, mode):
+        return [(Fp.double(), Ci) for Fp, Ci in parts], sum((Fp.shape[1] // 16) * (Ci * mode // 4) for Fp, Ci in parts)
+
+    launched = []
+
+    def zgemm(segs, w_img, sx, E, Co, mode, out, out_edge_stride, comp_off, flush_stages=0, alg_flops=0, tag=''):
+        launched.append(tag)
+        assert out_edge_stride == out.shape[1] * out.shape[2] and sx.shape == (E,)
+        planes = out.view(E, -1, Co)                           # component-major rows: plane index = comp_off / Co
+        res = [torch.zeros(E, Co, dtype=torch.float64) for _ in range(mode)]
+        si = 0
+        for Fp, Ci in w_img:
+            Kp = Fp.shape[1]
+            Fv = Fp.reshape(Co, Ci, mode, Kp)
+            for kc in range(Kp // 16):
+                U, X, Ci_s, ncomp, cplus, cminus = segs[si]
+                si += 1
+                assert Ci_s == Ci and X.shape == (E, Ci, ncomp) and U.shape[0] == E
+                w = torch.einsum('ek,oifk->eoif', U[:, :16].double(), Fv[..., 16 * kc:16 * kc + 16])
+                if mode == 1:
+                    res[0] += torch.einsum('eoi,ei->eo', w[..., 0], X[:, :, cplus])
+                else:
+                    a, bb_ = w[..., 0], w[..., 1]
+                    res[0] += torch.einsum('eoi,ei->eo', a, X[:, :, cplus]) - torch.einsum('eoi,ei->eo', bb_, X[:, :, cminus])
+                    res[1] += torch.einsum('eoi,ei->eo', bb_, X[:, :, cplus]) + torch.einsum('eoi,ei->eo', a, X[:, :, cminus])
+        assert si == len(segs)
+        for c in range(mode):
+            planes[:, comp_off[c] // Co, :] = res[c].float()
 
     def tbuild_blocks(x, idx, blocks, P, F, tile_begin=0, tile_count=None, out=None):
         bb, nn, Ci, Q = x.shape
@@ -193,8 +243,8 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
         e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
         return gather_rows(x, idx, e0, e1).unsqueeze(2)                             # [e, i, f = 1, q]
 
-    def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False):
-        res = torch.einsum('epqf,feoq->eop', basis_pair.reshape(E, P, Q, F).double(), S.double())
+    def fold_basis(S, basis_pair, E, Co, P, Q, F, out, accumulate, component_major=False, name='fold_basis'):
+        res = torch.einsum('epqf,feqo->eop' if component_major else 'epqf,feoq->eop', basis_pair.reshape(E, P, Q, F).double(), S.double())
         out.copy_((out.double() + res if accumulate else res).float())
 
     def pairwise_lr(U, img, T, E, Co, Ci, F, P, Kp, out, accumulate, alg_P=None, out_strides=None, p_off=None, alg_units=None):
@@ -214,7 +264,9 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
         out.copy_(torch.einsum('epn,eon->eop', D.reshape(E, P, P).double(), v).float())
 
     for name, fn in (('radial_trunk', radial_trunk), ('tbuild_blocks', tbuild_blocks), ('pairwise_lr', pairwise_lr),
-                     ('rotate_back', rotate_back), ('tbuild', tbuild), ('gather_tiles', gather_tiles), ('fold_basis', fold_basis)):
+                     ('rotate_back', rotate_back), ('tbuild', tbuild), ('gather_tiles', gather_tiles), ('fold_basis', fold_basis),
+                     ('radial_trunk_u', radial_trunk_u), ('rotgather', rotgather), ('edge_scale', edge_scale), ('zgemm_image', zgemm_image),
+                     ('zgemm', zgemm)):
         monkeypatch.setattr(ops, name, fn)
 
     coors = torch.randn(b, n, 3)
@@ -234,6 +286,7 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
     with torch.no_grad():
         out = M.conv_forward([conv], inp, (idx, nmask, None), rel_dist, basis)[0]
 
+    assert (len(launched) == 3 * (1 + 2 + 3)) == (frame == 'zgemm')       # 3 edge chunks x one launch per (degree_out, |m|)
     # reference order of operations in float64
     feat = rel_dist.reshape(E, 1).double()
     worst = 0.0
