@@ -164,6 +164,13 @@ int se3_frames_fwd(const float* rel_pos, int64_t E, int lmax, const double* cons
 int se3_rotgather_fwd(const float* x, const int64_t* idx, const float* D, int b, int n, int k, int Ci, int Q,
                       int64_t tile_begin, int64_t tile_count, float* X, void* stream);
 
+/* Pooled ConvSE3 epilogue (S:256-266, utils.py:72-80) fused with the rotation back to the global frame:
+ *   out[node,o,:] = masked_mean_j( D_lo(e_j) Oprime[e_j,:,o] ) + self_add[node,o,:],   e_j = node*K + j,
+ * Oprime [nodes*K, 2lo+1, Co] (component-major rows from se3_zgemm_fwd), D [nodes*K, 2lo+1, 2lo+1] (NULL for lo = 0),
+ * mask [nodes*K] or NULL (plain mean), self_add [nodes, Co, 2lo+1] or NULL (the LinearSE3 self-interaction), out [nodes, Co, 2lo+1]. */
+int se3_rotate_pool_fwd(const float* Oprime, const float* D, const uint8_t* mask, const float* self_add, int64_t nodes, int K,
+                        int Co, int lo, float* out, void* stream);
+
 /* out[row] = max_c |x[row, c]| (combine != 0: max with the value already in out); x [rows, W]. */
 int se3_rowabsmax_fwd(const float* x, int64_t rows, int W, int combine, float* out, void* stream);
 /* sx[e] = power of two with nodemax[b(e), idx[e]] * sqrt(2 max_degree + 1) * sx[e] < 2^10 (1 for all-zero nodes). */

@@ -170,6 +170,62 @@ edge_scale_kernel(const float* __restrict__ nodemax, const int64_t* __restrict__
   sx[e] = s;
 }
 
+// Pooled ConvSE3 epilogue (conv_in / conv_out; reference S:256-266, utils.py:72-80) fused with the rotation back to the global
+// frame: out[node,o,:] = masked_mean_j ( D_lo(e_j) out'[e_j,:,o] ) (+ self[node,o,:]), e_j = node*K + j.  The edge-level
+// [E, C, 2lo+1] tensor of the unfused path is never written.  Thread = (node, channel); D of 32 edges at a time in shared memory.
+constexpr int kRpEdges = 32;
+
+template <int P>
+__global__ void __launch_bounds__(256)
+rotate_pool_kernel(const float* __restrict__ Op, const float* __restrict__ D, const uint8_t* __restrict__ mask,
+                   const float* __restrict__ self_add, int K, int Co, float* __restrict__ out) {
+  __shared__ float sD[kRpEdges * P * P];
+  __shared__ uint8_t sM[kRpEdges];
+  const int64_t node = blockIdx.x;
+  const int o = blockIdx.y * blockDim.x + threadIdx.x;
+  float acc[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = 0.f;
+  int cnt = 0;
+  for (int j0 = 0; j0 < K; j0 += kRpEdges) {
+    const int nj = min(kRpEdges, K - j0);
+    const int64_t e0 = node * K + j0;
+    __syncthreads();
+    if (P > 1)
+      for (int t = threadIdx.x; t < nj * P * P; t += blockDim.x) sD[t] = D[e0 * P * P + t];
+    for (int t = threadIdx.x; t < nj; t += blockDim.x) sM[t] = mask ? mask[e0 + t] : (uint8_t)1;
+    __syncthreads();
+    for (int j = 0; j < nj; ++j) {
+      if (!sM[j]) continue;                       // uniform over the block
+      ++cnt;
+      if (o < Co) {
+        const float* src = Op + ((size_t)(e0 + j) * P) * Co + o;
+        float v[P];
+#pragma unroll
+        for (int n = 0; n < P; ++n) v[n] = src[(size_t)n * Co];
+        if (P == 1) {
+          acc[0] += v[0];
+        } else {
+          const float* d = sD + j * P * P;
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            float a = acc[p];
+#pragma unroll
+            for (int n = 0; n < P; ++n) a = fmaf(d[p * P + n], v[n], a);
+            acc[p] = a;
+          }
+        }
+      }
+    }
+  }
+  if (o >= Co) return;
+  const float inv = 1.f / (float)max(cnt, 1);     // masked_mean: sum / clamp(count, 1), zero when nothing is left (utils.py:76-79)
+  float* dst = out + ((size_t)node * Co + o) * P;
+  const float* sa = self_add ? self_add + ((size_t)node * Co + o) * P : nullptr;
+#pragma unroll
+  for (int p = 0; p < P; ++p) dst[p] = (cnt ? acc[p] * inv : 0.f) + (sa ? sa[p] : 0.f);
+}
+
 template <int Q>
 static void launch_rg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* D, int64_t E, int64_t tb, int n, int k,
                       int Ci, int cpc, float* X) {
@@ -218,6 +274,26 @@ extern "C" int se3_rotgather_fwd(const float* x, const int64_t* idx, const float
     case 7: launch_rg<7>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
     case 9: launch_rg<9>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
     default: launch_rg<11>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
+  }
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+extern "C" int se3_rotate_pool_fwd(const float* Oprime, const float* D, const uint8_t* mask, const float* self_add, int64_t nodes, int K,
+                                   int Co, int lo, float* out, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(nodes > 0 && K > 0 && Co > 0 && lo >= 0 && lo <= kMaxL, "se3_rotate_pool_fwd: bad sizes (degree_out 0..%d)", kMaxL);
+  SE3_REQUIRE(lo == 0 || D != nullptr, "se3_rotate_pool_fwd: D is required for degree > 0");
+  SE3_REQUIRE(nodes <= 2147483647ll && Co <= 65535 * 256, "se3_rotate_pool_fwd: too many nodes / channels");
+  dim3 grid((unsigned)nodes, (unsigned)ceil_div(Co, 256));
+  cudaStream_t s = as_stream(stream);
+  switch (lo) {
+    case 0: rotate_pool_kernel<1><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
+    case 1: rotate_pool_kernel<3><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
+    case 2: rotate_pool_kernel<5><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
+    case 3: rotate_pool_kernel<7><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
+    case 4: rotate_pool_kernel<9><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
+    default: rotate_pool_kernel<11><<<grid, 256, 0, s>>>(Oprime, D, mask, self_add, K, Co, out); break;
   }
   SE3_LAUNCH_OK();
   return SE3_OK;

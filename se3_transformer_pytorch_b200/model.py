@@ -542,6 +542,15 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         sx = ops.edge_scale(inp, idx, max(di for di, _ in c0.fiber_in))
         per_tile = sum(mi * to_order(di) for di, mi in c0.fiber_in) * ops.TILE_E * 4
         tpc = max(1, min(n_tiles, T_WORKSPACE_BYTES // per_tile))
+        # pooled convolutions (conv_in / conv_out): masked mean over the neighbours + self-interaction fused into the rotate-back
+        # (needs edge chunks that hold whole neighbour lists)
+        fuse_pool = tpc >= n_tiles or (tpc * ops.TILE_E) % k == 0
+        for st in z_states:
+            conv = st['conv']
+            if conv.pool and fuse_pool:
+                st['pooled'] = {do: torch.empty((b * n, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
+                st['self'] = conv.self_interact(inp) if conv.self_interaction else {}
+        nmask_flat = None if nmask is None else nmask.reshape(-1)
         for t0 in range(0, n_tiles, tpc):
             tc = min(tpc, n_tiles - t0)
             e0 = t0 * ops.TILE_E
@@ -552,7 +561,7 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 for do, mo in conv.fiber_out:
                     P = to_order(do)
                     full = all((do, m) in st['z'] for m in range(do + 1))
-                    if do == 0:
+                    if do == 0 and 'pooled' not in st:
                         Op = st['outs'][0][e0:e0 + ec]                   # [ec, mo, 1] is [ec, 1, mo]
                     else:
                         Op = (torch.empty if full else torch.zeros)((ec, P, mo), dtype=torch.float32, device=dev)
@@ -568,7 +577,12 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                             alg += ec * mo * mi * 2 * (ops.RADIAL_MID + P) * (1 if m == 0 else 2)
                         ops.zgemm(segs, zp['img'], sx[e0:e0 + ec], ec, mo, 1 if m == 0 else 2, Op, P * mo, [(do + m) * mo, (do - m) * mo],
                                   alg_flops=alg, tag=f'lo{do}m{m}Co{mo}S{zp["S"]}')
-                    if do > 0:                          # back to the global frame: out = D_lo out'
+                    if 'pooled' in st:                  # rotate back + masked mean over k + self-interaction, one kernel
+                        sa = st['self'].get(str(do))
+                        ops.rotate_pool(Op, frames.D[do][e0:e0 + ec] if do > 0 else None, None if nmask_flat is None else nmask_flat[e0:e0 + ec],
+                                        None if sa is None else sa.reshape(b * n, mo, P)[e0 // k:(e0 + ec) // k], ec // k, k, mo, do,
+                                        st['pooled'][do][e0 // k:(e0 + ec) // k])
+                    elif do > 0:                        # back to the global frame: out = D_lo out'
                         ops.fold_basis(Op.view(1, ec, P, mo), frames.D[do][e0:e0 + ec].reshape(-1), ec, mo, P, P, 1,
                                        st['outs'][do][e0:e0 + ec], accumulate=False, component_major=True, name='rotate_back')
             del X
@@ -660,6 +674,9 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
     for st in states_all:
         conv = st['conv']
         outputs = {}
+        if 'pooled' in st:
+            results.append({str(do): st['pooled'][do].view(b, n, mo, to_order(do)) for do, mo in conv.fiber_out})
+            continue
         for do, mo in conv.fiber_out:
             o = st['outs'][do].view(b, n, k, mo, to_order(do))
             if conv.pool:
@@ -744,7 +761,6 @@ class AttentionSE3(nn.Module):
             self.to_global_v = LinearSE3(gin, gout)
 
     def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
-        assert pos_emb is None, 'rotary embeddings are not part of the B200 hot path'
         forward_only_guard('AttentionSE3', [self], list(features.values()))
         idx, nmask, _ = edge_info
         queries = self.to_q(features)
@@ -762,6 +778,27 @@ class AttentionSE3(nn.Module):
             self_keys, self_values = self.to_self_k(features), self.to_self_v(features)
         if exists(global_feats):
             global_keys, global_values = self.to_global_k(global_feats), self.to_global_v(global_feats)
+        if exists(pos_emb):
+            # rotary embeddings on the type-0 queries / keys / values (reference S:488-494, 623-629; rotary.py:15-24): cheap
+            # elementwise glue in torch around the attention kernel.  The key embedding has 1 + k positions, self first.
+            assert self.attend_self, 'rotary embeddings need attend_self = True (the key positions include the node itself, as in the reference)'
+            q_emb, k_emb = pos_emb                                     # [b, n, rot], [b, n, 1 + k, rot]
+            b_, n_ = q_emb.shape[:2]
+            Dh, hk = self.dim_head, (1 if self.one_headed else self.heads)
+            queries = dict(queries)
+            queries['0'] = apply_rotary_pos_emb(queries['0'].view(b_, n_, self.heads, Dh, 1), q_emb[:, :, None, :, None]).reshape(b_, n_, -1, 1)
+            if k_idx is not None:                                      # linear_proj_keys: keys live on the nodes; rotary is per edge
+                keys = dict(keys)
+                keys['0'] = keys['0'][torch.arange(b_, device=idx.device)[:, None, None], idx]
+            nb_emb, self_emb = k_emb[:, :, 1:, None, :, None], k_emb[:, :, 0, None, :, None]
+            kk = idx.shape[-1]
+            new_k = apply_rotary_pos_emb(keys['0'].view(b_, n_, kk, hk, Dh, 1), nb_emb).reshape(b_, n_, kk, -1, 1)
+            new_v = new_k if values is keys else apply_rotary_pos_emb(values['0'].view(b_, n_, kk, hk, Dh, 1), nb_emb).reshape(b_, n_, kk, -1, 1)
+            keys, values = dict(keys), dict(values)
+            keys['0'], values['0'] = new_k, new_v
+            self_keys, self_values = dict(self_keys), dict(self_values)
+            self_keys['0'] = apply_rotary_pos_emb(self_keys['0'].view(b_, n_, hk, Dh, 1), self_emb).reshape(b_, n_, -1, 1)
+            self_values['0'] = apply_rotary_pos_emb(self_values['0'].view(b_, n_, hk, Dh, 1), self_emb).reshape(b_, n_, -1, 1)
         outputs = {}
         for degree in features.keys():
             kw = {}
@@ -773,9 +810,33 @@ class AttentionSE3(nn.Module):
             if exists(global_feats) and degree == '0':
                 kw.update(global_k=global_keys[degree], global_v=global_values[degree])
             outputs[degree] = ops.attention(queries[degree], keys[degree], values[degree], heads=self.heads, dim_head=self.dim_head,
-                                            scale=self.scale, nmask=nmask, k_idx=k_idx,
+                                            scale=self.scale, nmask=nmask, k_idx=(None if exists(pos_emb) and degree == '0' else k_idx),
                                             kv_heads=1 if self.one_headed else self.heads, **kw)
         return self.to_out(outputs)
+
+
+class SinusoidalEmbeddings(nn.Module):
+    """reference rotary.py:5-13"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.register_buffer('inv_freq', 1. / (10000 ** (torch.arange(0, dim, 2).float() / dim)))
+
+    def forward(self, t):
+        freqs = t[..., None].float() * self.inv_freq
+        return freqs.repeat_interleave(2, dim=-1)                      # '... d -> ... (d r)', r = 2
+
+
+def rotate_half(x):
+    """reference rotary.py:15-18 on [..., d, m]: pairs (x1, x2) of consecutive channels -> cat(-x2, x1) along d (NOT re-interleaved)."""
+    return torch.cat((-x[..., 1::2, :], x[..., 0::2, :]), dim=-2)
+
+
+def apply_rotary_pos_emb(t, freqs):
+    """reference rotary.py:20-24: t [..., d, m], freqs [..., rot, 1] (rot <= d leading channels are rotated)."""
+    rot = freqs.shape[-2]
+    tr, tp = t[..., :rot, :], t[..., rot:, :]
+    return torch.cat((tr * freqs.cos() + rotate_half(tr) * freqs.sin(), tp), dim=-2)
 
 
 class OneHeadedKVAttentionSE3(AttentionSE3):
@@ -827,8 +888,8 @@ def masked_mean_nodes(t, mask):
 class SE3Transformer(nn.Module):
     """Drop-in for se3_transformer_pytorch.SE3Transformer (reference S:936-1375), inference on B200.
 
-    Not carried over (raise NotImplementedError): reversible, use_egnn, rotary_position, rotary_rel_dist -- they are
-    outside the hot path named by BASELINE.json ("OUT OF SCOPE")."""
+    Not carried over (raise NotImplementedError): reversible, use_egnn -- they are outside the hot path named by BASELINE.json
+    ("OUT OF SCOPE")."""
 
     def __init__(self, *, dim, heads=8, dim_head=24, depth=2, input_degrees=1, num_degrees=None, output_degrees=1,
                  valid_radius=1e5, reduce_dim_out=False, num_tokens=None, num_positions=None, num_edge_tokens=None, edge_dim=None,
@@ -840,8 +901,7 @@ class SE3Transformer(nn.Module):
                  egnn_hidden_dim=32, egnn_weights_clamp_value=None, egnn_feedforward=False, hidden_fiber_dict=None,
                  out_fiber_dict=None):
         super().__init__()
-        for flag, name in ((reversible, 'reversible'), (use_egnn, 'use_egnn'), (rotary_position, 'rotary_position'),
-                           (rotary_rel_dist, 'rotary_rel_dist')):
+        for flag, name in ((reversible, 'reversible'), (use_egnn, 'use_egnn')):
             if flag:
                 raise NotImplementedError(f'{name}=True is outside the B200 hot path of this package')
         if differentiable_coors:
@@ -850,6 +910,10 @@ class SE3Transformer(nn.Module):
         self.dim_in = dim_in if isinstance(dim_in, tuple) else (dim_in,) * input_degrees
         self.dim = dim
         self.token_emb = nn.Embedding(num_tokens, dim) if exists(num_tokens) else None
+        self.rotary_rel_dist, self.rotary_position = rotary_rel_dist, rotary_position      # reference S:998-1004
+        self.rotary_pos_emb = None
+        if rotary_position or rotary_rel_dist:
+            self.rotary_pos_emb = SinusoidalEmbeddings(dim_head // (int(rotary_position) + int(rotary_rel_dist)))
         self.num_positions = num_positions
         self.pos_emb = nn.Embedding(num_positions, dim) if exists(num_positions) else None
         assert not (exists(num_edge_tokens) and not exists(edge_dim)), 'edge dimension (edge_dim) must be supplied if SE3 transformer is to have edge tokens'
@@ -1057,7 +1121,19 @@ class SE3Transformer(nn.Module):
         for conv, nonlin in self.convs:
             x = nonlin(x)
             x = conv(x, edge_info, rel_dist=rel_dist, basis=basis)
-        x = self.net(x, edge_info=edge_info, rel_dist=rel_dist, basis=basis, global_feats=global_feats, pos_emb=None, mask=_mask)
+        pos_emb = None
+        if exists(self.rotary_pos_emb):                         # reference S:1298-1325
+            q_parts, k_parts = [], []
+            if self.rotary_position:
+                seq_emb = self.rotary_pos_emb(torch.arange(n, device=device))                       # [n, d]
+                with_self = torch.cat((torch.arange(n, device=device).view(1, n, 1).expand(b, n, 1), idx), dim=2)
+                k_parts.append(seq_emb[with_self])                                                   # [b, n, 1 + k, d]
+                q_parts.append(seq_emb.unsqueeze(0).expand(b, n, -1))
+            if self.rotary_rel_dist:
+                k_parts.append(self.rotary_pos_emb(F.pad(rel_dist, (1, 0), value=0.) * 1e2))
+                q_parts.append(self.rotary_pos_emb(torch.zeros(n, device=device)).unsqueeze(0).expand(b, n, -1))
+            pos_emb = (torch.cat(q_parts, dim=-1), torch.cat(k_parts, dim=-1))
+        x = self.net(x, edge_info=edge_info, rel_dist=rel_dist, basis=basis, global_feats=global_feats, pos_emb=pos_emb, mask=_mask)
         if exists(self.conv_out):
             x = self.conv_out(x, edge_info, rel_dist=rel_dist, basis=basis)
         x = self.norm(x)

@@ -43,6 +43,7 @@ _SIGNATURES = {
     'se3_radial_trunk_u_fwd': (c_int, [c_void_p, c_int64, c_int, c_int] + [c_void_p] * 7),
     'se3_frames_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5),
     'se3_rotgather_fwd': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_int64, c_int64, c_void_p, c_void_p]),
+    'se3_rotate_pool_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_rowabsmax_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'se3_edge_scale_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_zgemm_tile_n': (c_int, [c_int, c_int]),
@@ -521,6 +522,17 @@ def rotgather(x, idx, D, tile_begin=0, tile_count=None, out=None):
     with torch.cuda.device(x.device), _timed('rotgather', flops=2 * Ec * Ci * Q * Q, nbytes=nbytes):
         _check(lib().se3_rotgather_fwd(_p(x), _p(idx.contiguous()), _p(D), b, n, k, Ci, Q, tile_begin, tile_count, _p(out), _stream()))
     return out
+
+
+def rotate_pool(Op, D, mask, self_add, nodes, K, Co, lo, out):
+    """Pooled ConvSE3 epilogue fused with the rotate-back: Op [nodes*K, 2lo+1, Co], D [nodes*K, P, P] or None (lo = 0),
+    mask [nodes*K] bool or None, self_add [nodes, Co, P] or None -> out [nodes, Co, P]."""
+    _require_cuda(Op, D, mask, self_add, out)
+    P = 2 * lo + 1
+    assert Op.is_contiguous() and out.is_contiguous() and (self_add is None or self_add.is_contiguous())
+    nbytes = 4 * (Op.numel() + out.numel() * (2 if self_add is not None else 1) + (nodes * K * P * P if lo else 0)) + nodes * K
+    with torch.cuda.device(out.device), _timed('rotate_pool', flops=2 * nodes * K * Co * P * P, nbytes=nbytes):
+        _check(lib().se3_rotate_pool_fwd(_p(Op), _p(D), _p(_u8(mask)), _p(self_add), nodes, K, Co, lo, _p(out), _stream()))
 
 
 def edge_scale(feats, idx, max_degree):

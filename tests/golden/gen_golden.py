@@ -131,6 +131,19 @@ ZCASES = [
 ]
 
 
+# rotary embeddings (reference rotary.py, S:488-494, 1298-1325; tests/test_equivariance.py:184-203)
+RCASES = [
+    dict(name='rotary_both', ctor=dict(dim=16, heads=2, dim_head=8, depth=1, attend_self=True, num_neighbors=4, num_degrees=2, output_degrees=2,
+                                       fourier_encode_dist=True, rotary_position=True, rotary_rel_dist=True), b=2, n=16),
+    dict(name='rotary_pos_onehead', ctor=dict(dim=16, heads=2, dim_head=8, depth=1, num_neighbors=4, num_degrees=2, rotary_position=True,
+                                              one_headed_key_values=True, use_null_kv=True), b=1, n=16),
+    dict(name='rotary_dist_linkeys', ctor=dict(dim=16, heads=2, dim_head=8, depth=2, num_neighbors=5, num_degrees=3, rotary_rel_dist=True,
+                                               linear_proj_keys=True), b=1, n=12),
+    dict(name='rotary_tiekv', ctor=dict(dim=16, heads=2, dim_head=12, depth=1, num_neighbors=4, num_degrees=2, rotary_position=True,
+                                        rotary_rel_dist=True, tie_key_values=True), b=1, n=12),
+]
+
+
 def build_inputs(case):
     b, n = case['b'], case['n']
     name = case['name']
@@ -277,10 +290,10 @@ if __name__ == '__main__':
         gen_sh_basis()
     if 'rot' in which:
         gen_equivariance_inputs()
-    if 'models' in which or 'big' in which or 'z' in which:
+    if 'models' in which or 'big' in which or 'z' in which or 'rotary' in which:
         kpath = os.path.join(HERE, 'state_keys.json')
         all_keys = json.load(open(kpath)) if os.path.exists(kpath) else {}
-        for case in (CASES if 'models' in which else []) + (BIG_CASES if 'big' in which else []) + (ZCASES if 'z' in which else []):
+        for case in (CASES if 'models' in which else []) + (BIG_CASES if 'big' in which else []) + (ZCASES if 'z' in which else []) + (RCASES if 'rotary' in which else []):
             all_keys[case['name']] = run_case(case)
         with open(kpath, 'w') as f:
             json.dump(all_keys, f, indent=0, sort_keys=True)

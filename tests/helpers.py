@@ -7,7 +7,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 MODEL_CASES = ['cfg1', 'deg4', 'af2', 'edges_sparse', 'ragged', 'tc_deg2', 'tc_deg4', 'allnbr', 'causal', 'tiekv',
                'linkeys', 'nullkv', 'noself', 'global', 'onehead', 'preconv_normout', 'tokens_pos', 'adjdeg', 'nbrmask',
-               'contedges']
+               'contedges', 'rotary_both', 'rotary_pos_onehead', 'rotary_dist_linkeys', 'rotary_tiekv']
 
 # BASELINE.json configs[2] at full size, configs[3] at batch 2 (the reference needs ~8 GB of host RAM per cloud there)
 BIG_CASES = ['cfg3', 'cfg4_b2']

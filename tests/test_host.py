@@ -45,7 +45,7 @@ def test_constructor_assertions_match_reference():
         SE3Transformer(dim=8, num_degrees=2, causal=True, attend_self=False)
     with pytest.raises(AssertionError):          # reference S:416
         SE3Transformer(dim=8, num_degrees=2, linear_proj_keys=True, tie_key_values=True)
-    for flag in ('reversible', 'use_egnn', 'rotary_position', 'rotary_rel_dist'):
+    for flag in ('reversible', 'use_egnn', 'differentiable_coors'):
         with pytest.raises(NotImplementedError):
             SE3Transformer(dim=8, num_degrees=2, **{flag: True})
 
