@@ -198,12 +198,37 @@ radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, con
   __syncthreads();
   // residual of the cached basis on these edges: thread t = hidden unit
   float rmax = 0.f, gmax = 0.f;
-  for (int e = 0; e < ne; ++e) {
-    float rec = 0.f;
-    for (int k = 0; k < rcol; ++k) rec = fmaf(fs[e][k], Vs[t * kVPad + k], rec);
-    const float gv = h[e][t];
-    rmax = fmaxf(rmax, fabsf(gv - rec));
-    gmax = fmaxf(gmax, fabsf(gv));
+  if (rcol <= 32) {
+    // this thread's row of V in registers; U rows are read as broadcast float4
+    float vr[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) vr[k] = (k < rcol) ? Vs[t * kVPad + k] : 0.f;
+    const int k4 = (rcol + 3) >> 2;
+    for (int e = 0; e < ne; ++e) {
+      float rec = 0.f;
+      const float4* ur = reinterpret_cast<const float4*>(&fs[e][0]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < k4) {
+          const float4 u = ur[q];
+          rec = fmaf(u.x, vr[4 * q], rec);
+          rec = fmaf(u.y, vr[4 * q + 1], rec);
+          rec = fmaf(u.z, vr[4 * q + 2], rec);
+          rec = fmaf(u.w, vr[4 * q + 3], rec);
+        }
+      }
+      const float gv = h[e][t];
+      rmax = fmaxf(rmax, fabsf(gv - rec));
+      gmax = fmaxf(gmax, fabsf(gv));
+    }
+  } else {
+    for (int e = 0; e < ne; ++e) {
+      float rec = 0.f;
+      for (int k = 0; k < rcol; ++k) rec = fmaf(fs[e][k], Vs[t * kVPad + k], rec);
+      const float gv = h[e][t];
+      rmax = fmaxf(rmax, fabsf(gv - rec));
+      gmax = fmaxf(gmax, fabsf(gv));
+    }
   }
   rmax = warp_max(rmax);
   gmax = warp_max(gmax);

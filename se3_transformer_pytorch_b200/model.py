@@ -341,8 +341,9 @@ class ConvSE3(nn.Module):
                         degs = [(di, mi) for di, mi in self.fiber_in if di >= m]
                         if not degs:
                             continue
-                        img, S = ops.zgemm_image([(fps.pop((di, do, m)), mi) for di, mi in degs], mo, 1 if m == 0 else 2)
-                        zplan[(do, m)] = dict(img=img, S=S, degs=degs)
+                        mode = 1 if m == 0 else z_mode_m()
+                        img, S = ops.zgemm_image([(fps.pop((di, do, m)), mi) for di, mi in degs], mo, mode)
+                        zplan[(do, m)] = dict(img=img, S=S, degs=degs, mode=mode)
                 del fps
         plan = dict(D=D, pairs=pairs, z=zplan)
         pk['lr'] = plan
@@ -408,6 +409,11 @@ def input_side(di, do):
 def use_zgemm():
     """One GEMM per (degree_out, |m|) with the A operand generated on the fly instead of the R-first kernels."""
     return not os.environ.get('SE3B200_NO_ZGEMM')
+
+
+def z_mode_m():
+    """Kernel mode of the |m| > 0 launches: 3 = three real products per complex one (Gauss; 3/4 of the tensor-core work of mode 2)."""
+    return 2 if os.environ.get('SE3B200_Z_MODE2') else 3
 
 
 def use_aligned():
@@ -575,8 +581,8 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                             for kc in range(st['lr'][(di, do)]['Kp'] // 16):
                                 segs.append((st['U'][pi, e0:e0 + ec, 16 * kc:], X[di], mi, to_order(di), di + m, di - m))
                             alg += ec * mo * mi * 2 * (ops.RADIAL_MID + P) * (1 if m == 0 else 2)
-                        ops.zgemm(segs, zp['img'], sx[e0:e0 + ec], ec, mo, 1 if m == 0 else 2, Op, P * mo, [(do + m) * mo, (do - m) * mo],
-                                  alg_flops=alg, tag=f'lo{do}m{m}Co{mo}S{zp["S"]}')
+                        ops.zgemm(segs, zp['img'], sx[e0:e0 + ec], ec, mo, zp['mode'], Op, P * mo, [(do + m) * mo, (do - m) * mo],
+                                  alg_flops=alg, tag=f'mode{zp["mode"]}lo{do}m{m}Co{mo}S{zp["S"]}')
                     if 'pooled' in st:                  # rotate back + masked mean over k + self-interaction, one kernel
                         sa = st['self'].get(str(do))
                         ops.rotate_pool(Op, frames.D[do][e0:e0 + ec] if do > 0 else None, None if nmask_flat is None else nmask_flat[e0:e0 + ec],

@@ -555,10 +555,11 @@ def zgemm_tile_n(Co, mode):
 
 
 def zgemm_image(parts, Co, mode):
-    """parts: [(Fp [Co*Ci*F, Kp] fp32, Ci)] in K order (one entry per input degree; Kp / 16 sub-segments each, F = mode) ->
-    (uint8 image, total_stages)."""
-    F = mode
-    stages = [(Fp.shape[1] // 16) * (Ci * F // 4) for Fp, Ci in parts]
+    """parts: [(Fp [Co*Ci*F, Kp] fp32, Ci)] in K order (one entry per input degree; Kp / 16 sub-segments each; F = 1 for mode 1,
+    rows (o, i, (a, b)) for modes 2 and 3) -> (uint8 image, total_stages)."""
+    F = 1 if mode == 1 else 2
+    per_seg = (lambda Ci: 3 * (Ci // 4)) if mode == 3 else (lambda Ci: Ci * F // 4)
+    stages = [(Fp.shape[1] // 16) * per_seg(Ci) for Fp, Ci in parts]
     S = sum(stages)
     nbytes = lib().se3_zgemm_image_bytes(Co, mode, S)
     if nbytes < 0:
@@ -574,7 +575,7 @@ def zgemm_image(parts, Co, mode):
             assert Fp.shape[0] == Co * Ci * F and Kp % 16 == 0 and (Ci * F) % 4 == 0
             for kc in range(Kp // 16):
                 _check(lib().se3_zgemm_pack(_p(Fp), Kp, 16 * kc, Co, Ci * F, mode, S, s0, _p(img), _stream()))
-                s0 += Ci * F // 4
+                s0 += per_seg(Ci)
     return img, S
 
 
@@ -587,10 +588,13 @@ def zgemm(segs, w_img, sx, E, Co, mode, out, out_edge_stride, comp_off, flush_st
         _require_cuda(U, X)
         assert U.dtype == torch.float32 and U.stride(-1) == 1 and (U.dim() == 1 or U.stride(0) == 64)
         arr[i] = ZSeg(U.data_ptr(), X.data_ptr(), Ci, ncomp, cplus, cminus)
-        Ktot += Ci * mode * 16
+        Ktot += Ci * (1, 2, 3)[mode - 1] * 16
     N = zgemm_tile_n(Co, mode)
-    mma = 2 * E * Co * Ktot * 3 * mode                   # issued: 3 fp16 passes; mode 2 feeds two accumulators from every B tile
-    nbytes = w_img.numel() + 4 * E * Co * mode + sum(4 * E * s[2] * (mode + 16) for s in segs)
+    # issued tensor-core FLOPs: 3 fp16 passes of 2 M N K; mode 2 feeds two accumulators from every B tile, mode 3 has three
+    # weight sets with one accumulator each
+    mma = 2 * E * Co * Ktot * 3 * (2 if mode == 2 else 1)
+    planes = 1 if mode == 1 else 2
+    nbytes = w_img.numel() + 4 * E * Co * planes + sum(4 * E * s[2] * (planes + 16) for s in segs)
     with torch.cuda.device(out.device), _timed('zgemm', flops=alg_flops, nbytes=nbytes, tag=tag or f'mode{mode}N{N}K{Ktot}', mma=mma):
         _check(lib().se3_zgemm_fwd(arr, len(segs), _p(w_img), _p(sx), E, Co, mode, _p(out), out_edge_stride, comp_off[0],
                                    comp_off[1] if len(comp_off) > 1 else 0, flush_stages, _stream()))

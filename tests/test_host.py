@@ -192,12 +192,14 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
         return torch.full((idx.numel(),), 4.0)
 
     def zgemm_image(parts, Co, mode):
-        return [(Fp.double(), Ci) for Fp, Ci in parts], sum((Fp.shape[1] // 16) * (Ci * mode // 4) for Fp, Ci in parts)
+        per_seg = (lambda Ci: 3 * (Ci // 4)) if mode == 3 else (lambda Ci: Ci * min(mode, 2) // 4)
+        return [(Fp.double(), Ci) for Fp, Ci in parts], sum((Fp.shape[1] // 16) * per_seg(Ci) for Fp, Ci in parts)
 
     launched = []
 
     def zgemm(segs, w_img, sx, E, Co, mode, out, out_edge_stride, comp_off, flush_stages=0, alg_flops=0, tag=''):
         launched.append(tag)
+        mode = min(mode, 2)                                    # mode 3 = mode 2 evaluated with three products per complex one
         assert out_edge_stride == out.shape[1] * out.shape[2] and sx.shape == (E,)
         planes = out.view(E, -1, Co)                           # component-major rows: plane index = comp_off / Co
         res = [torch.zeros(E, Co, dtype=torch.float64) for _ in range(mode)]
