@@ -144,12 +144,13 @@ int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int
  * (degree_out, |m|) (the same product S:237-254, 326-343 re-associated) ------------------------------------ */
 
 /* Radial trunk as se3_radial_trunk_fwd, followed in the same kernel by the low-rank radial coordinates of every pair:
- *   out_U [num_pairs, E, 64]: columns 0..r-1 = g V, column r = 1 (bias slot), rest 0, r = ones_col[pair], V [num_pairs,128,64]
- *   (columns >= r zero);  stats [num_pairs, 2] (caller zeroes it): (max |g - U V^T|, max |g|) over the edges, accumulated with
+ *   out_U [num_pairs, E, 64]: columns 0..r-1 = (g - gmean) V, column r = 1 (bias slot), rest 0, r = ones_col[pair],
+ *   V [num_pairs,128,64] (columns >= r zero), gmean [num_pairs,128] the centre of the pair's radial curve (W3 gmean is part of the
+ *   bias column of F');  stats [num_pairs, 2] (caller zeroes it): (max |g - gmean - U V^T|, max |g|) over the edges, accumulated with
  *   atomicMax -- the run-time check that the cached basis covers this forward's distances, read by the host once per forward.
  *   out_g may be NULL. */
 int se3_radial_trunk_u_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params, const float* V,
-                           const int* ones_col, float* out_g, float* out_U, float* stats, void* stream);
+                           const float* gmean, const int* ones_col, float* out_g, float* out_U, float* stats, void* stream);
 
 /* Per-edge frames: R_e takes the polar axis a = (0,1,0) of the reference's harmonics (basis.py:57-95) to the direction of
  * rel_pos[e]; D_out[l] [E, 2l+1, 2l+1] = real Wigner matrix D_l(R_e) in the reference's basis, l = 1..lmax <= 5, computed in

@@ -103,16 +103,16 @@ radial_trunk_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const
 }
 
 // Trunk + low-rank radial coordinates: the same trunk, followed in the same CTA by
-//   U[e, 0..r-1] = g[e,:] V[:, 0..r-1],   U[e, r] = 1 (bias slot),   U[e, r+1..63] = 0
-// with the pair's cached orthonormal basis V [128, 64] (columns >= r are zero), and by the check of that basis on the edges of
-// THIS forward: stats[pair] = (max |g - U V^T|, max |g|) accumulated with atomicMax (non-negative floats order like their bit
+//   U[e, 0..r-1] = (g[e,:] - gmean) V[:, 0..r-1],   U[e, r] = 1 (bias slot),   U[e, r+1..63] = 0
+// with the pair's cached centre gmean [128] and orthonormal basis V [128, 64] (columns >= r are zero), and by the check of that
+// affine model on the edges of THIS forward: stats[pair] = (max |g - gmean - U V^T|, max |g|) accumulated with atomicMax (non-negative floats order like their bit
 // patterns), read by the host once per forward.  g itself is only written when out_g != NULL.
 constexpr int kVPad = 65;
 
 __global__ void __launch_bounds__(128)
 radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, const float* __restrict__ params, int64_t param_stride,
-                      const float* __restrict__ Vall, const int* __restrict__ ones_col, float* __restrict__ out_g,
-                      float* __restrict__ out_U, float* __restrict__ stats) {
+                      const float* __restrict__ Vall, const float* __restrict__ gmean, const int* __restrict__ ones_col,
+                      float* __restrict__ out_g, float* __restrict__ out_U, float* __restrict__ stats) {
   extern __shared__ __align__(16) float dsm[];
   float (*h)[kMid + 4] = reinterpret_cast<float (*)[kMid + 4]>(dsm);                    // [32][132]
   float (*fs)[64] = reinterpret_cast<float (*)[64]>(dsm + kTrunkEB * (kMid + 4));       // [32][64]; reused for U
@@ -179,7 +179,18 @@ radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, con
     float* og = out_g + ((size_t)pair * E + e0) * kMid;
     for (int e = 0; e < ne; ++e) og[(size_t)e * kMid + t] = h[e][t];
   }
-  // U = g V: thread t -> column k = t % 64 for 16 of the 32 edges
+  // centre: the low-rank model is affine, g ~= gmean + U V^T (W3 gmean rides in the bias column of F'); max |g| before centring
+  float gmax = 0.f;
+  {
+    const float mu = gmean[(size_t)pair * kMid + t];
+    for (int e = 0; e < ne; ++e) {
+      const float gv = h[e][t];
+      gmax = fmaxf(gmax, fabsf(gv));
+      h[e][t] = gv - mu;
+    }
+  }
+  __syncthreads();
+  // U = (g - gmean) V: thread t -> column k = t % 64 for 16 of the 32 edges
   {
     const int k = t & 63, eh = (t >> 6) * 16;
     float acc[16];
@@ -197,7 +208,7 @@ radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, con
   }
   __syncthreads();
   // residual of the cached basis on these edges: thread t = hidden unit
-  float rmax = 0.f, gmax = 0.f;
+  float rmax = 0.f;
   if (rcol <= 32) {
     // this thread's row of V in registers; U rows are read as broadcast float4
     float vr[32];
@@ -217,17 +228,13 @@ radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, con
           rec = fmaf(u.w, vr[4 * q + 3], rec);
         }
       }
-      const float gv = h[e][t];
-      rmax = fmaxf(rmax, fabsf(gv - rec));
-      gmax = fmaxf(gmax, fabsf(gv));
+      rmax = fmaxf(rmax, fabsf(h[e][t] - rec));
     }
   } else {
     for (int e = 0; e < ne; ++e) {
       float rec = 0.f;
       for (int k = 0; k < rcol; ++k) rec = fmaf(fs[e][k], Vs[t * kVPad + k], rec);
-      const float gv = h[e][t];
-      rmax = fmaxf(rmax, fabsf(gv - rec));
-      gmax = fmaxf(gmax, fabsf(gv));
+      rmax = fmaxf(rmax, fabsf(h[e][t] - rec));
     }
   }
   rmax = warp_max(rmax);
@@ -246,16 +253,16 @@ radial_trunk_u_kernel(const float* __restrict__ feat, int64_t E, int in_dim, con
 }  // namespace se3
 
 extern "C" int se3_radial_trunk_u_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params, const float* V,
-                                      const int* ones_col, float* out_g, float* out_U, float* stats, void* stream) {
+                                      const float* gmean, const int* ones_col, float* out_g, float* out_U, float* stats, void* stream) {
   using namespace se3;
   SE3_REQUIRE(E > 0 && num_pairs > 0, "se3_radial_trunk_u_fwd: bad sizes");
   SE3_REQUIRE(in_dim >= 1 && in_dim <= 64, "se3_radial_trunk_u_fwd: in_dim %d unsupported (1..64)", in_dim);
-  SE3_REQUIRE(V != nullptr && ones_col != nullptr && out_U != nullptr && stats != nullptr, "se3_radial_trunk_u_fwd: null pointer");
+  SE3_REQUIRE(V != nullptr && gmean != nullptr && ones_col != nullptr && out_U != nullptr && stats != nullptr, "se3_radial_trunk_u_fwd: null pointer");
   const int64_t param_stride = (int64_t)in_dim * kMid + 3 * kMid + kMid * kMid + 3 * kMid;
   const size_t smem = sizeof(float) * (kTrunkEB * (kMid + 4) + kTrunkEB * 64 + kMid * kVPad);
   SE3_CUDA_OK(cudaFuncSetAttribute(radial_trunk_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, kTrunkEB), (unsigned)num_pairs);
-  radial_trunk_u_kernel<<<grid, 128, smem, as_stream(stream)>>>(feat, E, in_dim, params, param_stride, V, ones_col, out_g, out_U, stats);
+  radial_trunk_u_kernel<<<grid, 128, smem, as_stream(stream)>>>(feat, E, in_dim, params, param_stride, V, gmean, ones_col, out_g, out_U, stats);
   SE3_LAUNCH_OK();
   return SE3_OK;
 }

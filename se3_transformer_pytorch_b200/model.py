@@ -293,13 +293,13 @@ class ConvSE3(nn.Module):
             if aligned_images and use_zgemm() and self.zgemm_eligible({pair: 16 * ((rv[0] + 1 + 15) // 16) for pair, rv in bases.items()}):
                 zplan = {}                    # (do, m) -> dict(img, degs): one GEMM per output degree and |m|
                 fps = {}
-            for (di, do), (r, V) in bases.items():
+            for (di, do), (r, V, gmean) in bases.items():
                 pc = self.kernel_unary[f'({di},{do})']
                 lin = pc.rp.net['6']
                 Kp = 16 * ((r + 1 + 15) // 16)
                 Fp = torch.zeros((lin.weight.shape[0], Kp), dtype=torch.float32, device=dev)
                 Fp[:, :r] = (lin.weight.double() @ V).float()
-                Fp[:, r] = lin.bias
+                Fp[:, r] = (lin.bias.double() + lin.weight.double() @ gmean).float()      # affine model: W3 gmean joins the bias
                 Vp = torch.zeros((ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
                 Vp[:, :r] = V.float()
                 if zplan is not None:
@@ -311,7 +311,7 @@ class ConvSE3(nn.Module):
                     for m in range(1, min(di, do) + 1):
                         ab = torch.stack([torch.einsum('oifk,f->oik', Fv, ca[m - 1]), torch.einsum('oifk,f->oik', Fv, cb[m - 1])], dim=2)
                         fps[(di, do, m)] = ab.reshape(-1, Kp).float().contiguous()
-                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=None, al_imgs=None, z=True)
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, gmean=gmean.float(), img=None, imgs_f=None, al_imgs=None, z=True)
                     del Fv
                 elif aligned_images:
                     # edge-aligned formulation: images of the weights a_m, b_m = constant combinations of the
@@ -323,17 +323,17 @@ class ConvSE3(nn.Module):
                     for m in range(1, min(di, do) + 1):
                         ab = torch.stack([torch.einsum('oifk,f->oik', Fv, ca[m - 1]), torch.einsum('oifk,f->oik', Fv, cb[m - 1])], dim=2)
                         imgs.append(ops.pack_lowrank(ab.reshape(-1, Kp).float().contiguous(), pc.nc_out, pc.nc_in, 2, Kp))
-                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=None, al_imgs=imgs)
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, gmean=gmean.float(), img=None, imgs_f=None, al_imgs=imgs)
                     del Fv
                 elif input_side(di, do) and pc.num_freq > 1:
                     # input-side contraction: one image per frequency f (rows (o,i,f) of F'), no combined image
                     Fv = Fp.view(pc.nc_out, pc.nc_in, pc.num_freq, Kp)
                     imgs = [ops.pack_lowrank(Fv[:, :, f, :].reshape(-1, Kp).contiguous(), pc.nc_out, pc.nc_in, 1, Kp)
                             for f in range(pc.num_freq)]
-                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=None, imgs_f=imgs)
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, gmean=gmean.float(), img=None, imgs_f=imgs)
                 else:
                     img = ops.pack_lowrank(Fp, pc.nc_out, pc.nc_in, pc.num_freq, Kp)
-                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, img=img, imgs_f=[img] if pc.num_freq == 1 else None)
+                    pairs[(di, do)] = dict(r=r, Kp=Kp, V=Vp, gmean=gmean.float(), img=img, imgs_f=[img] if pc.num_freq == 1 else None)
                 del Fp
             if zplan is not None:
                 for do, mo in self.fiber_out:
@@ -499,19 +499,21 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
         if lr_plan is not None and lr_plan['pairs']:
             if 'Vstack' not in lr_plan:
                 Vs = torch.zeros((len(conv.pairs), ops.RADIAL_MID, 64), dtype=torch.float32, device=dev)
+                gm = torch.zeros((len(conv.pairs), ops.RADIAL_MID), dtype=torch.float32, device=dev)
                 ones_col = torch.zeros(len(conv.pairs), dtype=torch.int32, device=dev)
                 have = torch.zeros(len(conv.pairs), dtype=torch.bool, device=dev)
                 for pi, pair in enumerate(conv.pairs):
                     pp = lr_plan['pairs'].get(pair)
                     if pp is not None:
                         Vs[pi] = pp['V']
+                        gm[pi] = pp['gmean']
                         ones_col[pi] = pp['r']
                         have[pi] = True
-                lr_plan['Vstack'], lr_plan['ones_col'], lr_plan['have'] = Vs, ones_col, have
+                lr_plan['Vstack'], lr_plan['gmean'], lr_plan['ones_col'], lr_plan['have'] = Vs, gm, ones_col, have
             # trunk + U = G V + the residual statistics of the cached subspace on THIS forward's edges, one kernel
             covered = len(lr_plan['pairs']) == len(conv.pairs)
             stats = torch.zeros((len(conv.pairs), 2), dtype=torch.float32, device=dev)
-            U, g = ops.radial_trunk_u(feat, pk['trunk'], lr_plan['Vstack'], lr_plan['ones_col'], stats, want_g=not covered)
+            U, g = ops.radial_trunk_u(feat, pk['trunk'], lr_plan['Vstack'], lr_plan['gmean'], lr_plan['ones_col'], stats, want_g=not covered)
             for pi, pair in enumerate(conv.pairs):
                 pp = lr_plan['pairs'].get(pair)
                 if pp is not None:

@@ -193,15 +193,17 @@ def test_radial_trunk_u():
         q, _ = torch.linalg.qr(torch.randn(128, r[p], generator=g))
         V[p, :, :r[p]] = q.to(DEV)
     ones_col = torch.tensor(r, dtype=torch.int32, device=DEV)
+    gmean = g_ref.mean(dim=1).contiguous()                   # the centre of the affine model
     stats = torch.zeros(pairs, 2, device=DEV)
-    U, g_out = ops.radial_trunk_u(feat, params, V, ones_col, stats, want_g=True)
+    U, g_out = ops.radial_trunk_u(feat, params, V, gmean, ones_col, stats, want_g=True)
     assert torch.equal(g_out, g_ref)
     for p in range(pairs):
-        ref = g_ref[p].double() @ V[p].double()
+        gc = g_ref[p].double() - gmean[p].double()
+        ref = gc @ V[p].double()
         assert float((U[p, :, :r[p]] - ref[:, :r[p]]).abs().max()) < 1e-5
         assert bool((U[p, :, r[p]] == 1).all()) and float(U[p, :, r[p] + 1:].abs().max()) == 0.0
-        resid = (g_ref[p].double() - ref @ V[p].double().t()).abs().max()
+        resid = (gc - ref @ V[p].double().t()).abs().max()
         assert abs(float(stats[p, 0]) - float(resid)) < 1e-5 * max(1.0, float(resid))
         assert abs(float(stats[p, 1]) - float(g_ref[p].abs().max())) < 1e-6
-    U2, none = ops.radial_trunk_u(feat, params, V, ones_col, stats)
+    U2, none = ops.radial_trunk_u(feat, params, V, gmean, ones_col, stats)
     assert none is None and torch.equal(U2, U)

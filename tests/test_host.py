@@ -173,10 +173,11 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
     def radial_trunk(feat, params, num_pairs):
         return torch.stack([conv.kernel_unary[f'({di},{do})'].rp.trunk64(feat.double()) for di, do in conv.pairs]).float()
 
-    def radial_trunk_u(feat, params, V, ones_col, stats, want_g=False):
+    def radial_trunk_u(feat, params, V, gmean, ones_col, stats, want_g=False):
         g = radial_trunk(feat, params, len(conv.pairs)).double()
-        U = torch.bmm(g, V.double())
-        resid = (g - torch.bmm(U, V.double().transpose(1, 2))).abs().amax(dim=(1, 2))
+        gc = g - gmean.double()[:, None, :]
+        U = torch.bmm(gc, V.double())
+        resid = (gc - torch.bmm(U, V.double().transpose(1, 2))).abs().amax(dim=(1, 2))
         stats[:, 0] = torch.maximum(stats[:, 0], resid.float())
         stats[:, 1] = torch.maximum(stats[:, 1], g.abs().amax(dim=(1, 2)).float())
         U[torch.arange(len(conv.pairs)), :, ones_col.long()] = 1.0
