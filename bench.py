@@ -30,6 +30,8 @@ WORKLOADS = {
     'cfg2': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=6, num_degrees=4, num_neighbors=16), b=4, n=1024),
     'cfg3': dict(ctor=dict(dim=64, depth=2, input_degrees=1, num_degrees=2, output_degrees=2, reduce_dim_out=True, num_neighbors=16),
                  b=2, n=256, fwd=dict(return_type=1)),
+    'cfg4': dict(ctor=dict(dim=128, depth=2, num_degrees=3, num_edge_tokens=4, edge_dim=16, attend_sparse_neighbors=True, num_neighbors=0,
+                           max_sparse_neighbors=8), b=8, n=512, edges='tokens', adj=4),
     'cfg5': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=6, num_degrees=4, num_neighbors=32), b=8, n=2048),
     # reduced-width variants for quick iteration (NOT the headline)
     'cfg2_d128': dict(ctor=dict(dim=128, heads=8, dim_head=16, depth=6, num_degrees=4, num_neighbors=16), b=4, n=1024),
@@ -66,9 +68,16 @@ def conv_flops(f_in, f_out, edges):
 
 def forward_flops(wl):
     c = wl['ctor']
-    k = min(c['num_neighbors'], wl['n'] - 1)
-    edges = wl['b'] * wl['n'] * k
+    edges = wl['b'] * wl['n'] * neighbours(wl)
     return sum(conv_flops(fi, fo, edges) for fi, fo in conv_list(c))
+
+
+def neighbours(wl):
+    c = wl['ctor']
+    k = int(min(c.get('num_neighbors', float('inf')), wl['n'] - 1))
+    if c.get('attend_sparse_neighbors'):
+        k += int(min(c.get('max_sparse_neighbors', 0), 2 * wl.get('adj', 0)))
+    return k
 
 
 def load_peaks():
@@ -95,7 +104,8 @@ class CpuSample:
         c = wl['ctor']
         nd, dim = c['num_degrees'], c['dim']
         hid = c.get('heads', 8) * c.get('dim_head', 24)
-        k = min(c['num_neighbors'], wl['n'] - 1)
+        k = neighbours(wl)
+        e_dim = c.get('edge_dim') or 0               # per-edge features next to the distance (BASELINE configs[3])
         self.f_in = [(d, dim) for d in range(nd)]
         self.f_out = [(d, hid) for d in range(nd)]
         per_edge = conv_flops(self.f_in, self.f_out, 1)
@@ -107,7 +117,7 @@ class CpuSample:
             for do, co in self.f_out:
                 f = 2 * min(di, do) + 1
                 pp = f'to_v.kernel_unary.({di},{do}).rp.'
-                P[pp + 'net.0.weight'] = rng.standard_normal((128, 1), dtype=np.float32)
+                P[pp + 'net.0.weight'] = rng.standard_normal((128, 1 + e_dim), dtype=np.float32)
                 P[pp + 'net.0.bias'] = np.zeros(128, np.float32)
                 P[pp + 'net.1.weight'] = np.ones(128, np.float32)
                 P[pp + 'net.1.bias'] = np.zeros(128, np.float32)
@@ -124,6 +134,9 @@ class CpuSample:
         coors = rng.standard_normal((1, n, 3)).astype(np.float32)
         self.feats = {str(d): rng.standard_normal((1, n, ci, 2 * d + 1)).astype(np.float32) for d, ci in self.f_in}
         self.graph = O.neighbor_graph(coors, None, num_neighbors=k)
+        self.e_dim = e_dim
+        if e_dim:
+            self.graph['edges'] = rng.standard_normal((1, n, k, e_dim)).astype(np.float32)
         self.basis = O.get_basis(self.graph['rel_pos'], nd - 1)
         self.chunk = max(1, int(2 ** 28 // (hid * dim * (2 * (nd - 1) + 1))))
         self.E = n * k
@@ -149,7 +162,7 @@ class CpuSample:
         import torch
         from se3_transformer_pytorch_b200 import ops
         from se3_transformer_pytorch_b200.model import ConvSE3, Fiber, Geometry
-        conv = ConvSE3(Fiber(self.f_in), Fiber(self.f_out), pool=False, self_interaction=False)
+        conv = ConvSE3(Fiber(self.f_in), Fiber(self.f_out), pool=False, self_interaction=False, edge_dim=self.e_dim)
         sd = {k[len('to_v.'):]: torch.from_numpy(v) for k, v in self.P.items()}
         conv.load_state_dict(sd)
         conv = conv.to(dev).eval()
@@ -164,7 +177,7 @@ class CpuSample:
             with torch.no_grad():
                 rel_pos = t(g['rel_pos'])
                 basis = ops.basis_flat(rel_pos, nd - 1) + (Geometry(rel_pos, nd - 1),)
-                out = conv(inp, (t(g['idx']), t(g['mask']), None), t(g['rel_dist']), basis)
+                out = conv(inp, (t(g['idx']), t(g['mask']), t(g['edges']) if self.e_dim else None), t(g['rel_dist']), basis)
             torch.cuda.synchronize()
         finally:
             kinds = sorted({p[0] for p in ops.PROFILE})
@@ -279,7 +292,16 @@ def run_ours(args, wl, rank, local_rank, world):
     with torch.device(dev):
         model = SE3Transformer(**wl['ctor'])
     model.eval()
-    lowrank = ops.lowrank_enabled(wl['b'] * wl['n'] * min(wl['ctor']['num_neighbors'], wl['n'] - 1))
+    if args.global_batch:
+        assert args.global_batch % world == 0, '--global-batch must be divisible by the number of GPUs'
+        wl = dict(wl, b=args.global_batch // world)
+    if args.radial_scale != 1.0:
+        # weights-sensitivity experiment: a less smooth radial MLP (first-layer weights scaled up) needs a higher rank
+        with torch.no_grad():
+            for m in model.conv_modules():
+                for pc in m.kernel_unary.values():
+                    pc.rp.net['0'].weight.mul_(args.radial_scale)
+    lowrank = ops.lowrank_enabled(wl['b'] * wl['n'] * neighbours(wl)) and not wl['ctor'].get('edge_dim')
     # tensor-core operand images (low-rank plan for distances <= 16 where the radial functions are distance-only, the
     # direct K=128 image otherwise); fp32 masters of net.6 released (inference)
     model.pack_weights(free_master=True, max_distance=16.0 if lowrank else None)
@@ -292,6 +314,10 @@ def run_ours(args, wl, rank, local_rank, world):
     h_feats = torch.randn(b, n, dim, generator=g).pin_memory()
     h_coors = torch.randn(b, n, 3, generator=g).pin_memory()
     h_mask = torch.ones(b, n, dtype=torch.bool).pin_memory()
+    if wl.get('edges') == 'tokens':                      # BASELINE configs[3]: edge tokens + band adjacency (|i - j| <= adj bonded neighbours)
+        seq = torch.arange(n)
+        fwd_kw = dict(fwd_kw, edges=torch.randint(0, wl['ctor']['num_edge_tokens'], (b, n, n), generator=g).to(dev),
+                      adj_mat=((seq[:, None] - seq[None, :]).abs() <= wl['adj']).to(dev))
 
     graphed = None
     if args.cuda_graph:
@@ -434,12 +460,12 @@ def run_ours(args, wl, rank, local_rank, world):
         parity = sample.gpu_parity(dev)
     line = {
         'metric': 'point-clouds/sec fwd', 'value': value, 'unit': 'clouds/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': args.workload, **wl['ctor'], 'batch_per_gpu': b, 'global_batch': b * world, 'n_points': n,
                    'parallelism': f'dp{world} (batch sharded, replicated weights, one all-gather of outputs)',
                    'cache': f'inputs larger than L2: every step streams the {weights_gb:.1f} GB of weight images and the per-layer T / K / V tensors (several GB each)', 'weights_resident_gb': weights_gb, 'random_init': True, 'cuda_graph': bool(args.cuda_graph), 'lowrank_radial': bool(lowrank),
-                   'flops_per_cloud': forward_flops(wl) / b, 'model_build_s': t_build},
+                   'flops_per_cloud': forward_flops(wl) / b, 'model_build_s': t_build, 'radial_scale': args.radial_scale},
         'e2e': {'value': e2e, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
         'clocks': clocks,
@@ -467,6 +493,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-flops', type=float, default=3e11, help='size of the bounded CPU sample (algorithmic FLOPs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--global-batch', type=int, default=0, help='STRONG scaling: fixed global batch split over the ranks (default: weak scaling, the workload batch per rank)')
+    ap.add_argument('--radial-scale', type=float, default=1.0, help='weights-sensitivity experiment: scale RadialFunc.net.0.weight (rougher radial functions, higher rank)')
     ap.add_argument('--cuda-graph', action='store_true', help='replay the forward from a CUDA graph (launch-bound small workloads)')
     ap.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the resident timed steps (for ncu --profile-from-start off)')
     args = ap.parse_args()

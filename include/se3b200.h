@@ -218,6 +218,27 @@ int se3_attn_fwd(const float* q, const float* k, const float* v, const int64_t* 
                  const float* global_k, const float* global_v, int G, const uint8_t* nmask,
                  int b, int n, int K, int H, int Dh, int M, int kv_heads, float scale, float* out, void* stream);
 
+/* LinearSE3 (S:78-95) on the tensor cores: out[node, o, m] = sum_d x[node, d, m] W[d, o] (+ res[node, o, m]); x [nodes, D, M] and
+ * out / res [nodes, Eo, M] in the reference layout (no transposed copies), 3-pass fp16 split with fp32 partial sums as in
+ * se3_zgemm_fwd.  w_img = se3_zgemm_pack(Fp = W^T [Eo, D] viewed as [Eo * D/16, 16], Kp 16, col0 0, Co Eo, CiF D/16, mode 4,
+ * total_stages D/64, stage0 0) (se3_zgemm_image_bytes(Eo, 4, D/64) bytes).  sx [nodes]: se3_pow2_scale_fwd of the row maxima
+ * (se3_rowabsmax_fwd) with target exponent 14.  D % 64 == 0, Eo % 128 == 0.  res may be NULL. */
+int se3_linear_tc_fwd(const float* x, const void* w_img, const float* res, const float* sx, int64_t nodes, int D, int Eo, int M,
+                      float* out, void* stream);
+/* sx[r] = power of two with rowmax[r] * sx[r] in [2^(target_exp-1), 2^target_exp) (1 for zero / non-finite rows). */
+int se3_pow2_scale_fwd(const float* rowmax, int64_t rows, int target_exp, float* sx, void* stream);
+
+/* As se3_attn_fwd for degrees >= 1 when the values (and, with k_aligned != 0, the keys) are still in the edge-aligned frame:
+ * v (k) [b,n,K,M,Ckv] = the component-major out' of se3_zgemm_fwd, D [b*n*K, M, M] the frames of se3_frames_fwd,
+ * k[e,d,:] = D(e) k'[e,:,d].  The rotation back to the global frame (se3_rotate_back / fold_basis of the unfused path) happens
+ * inside the kernel, so the global-frame K / V tensors are never materialised.  With k_aligned == 0 the keys are in the
+ * global frame as for se3_attn_fwd (node level with k_idx, linear_proj_keys).  Prefix keys/values (self, null, global) are
+ * global-frame as before. */
+int se3_attn_aligned_fwd(const float* q, const float* k, const float* v, const float* D, int k_aligned, const int64_t* k_idx,
+                         const float* self_k, const float* self_v, const float* null_k, const float* null_v,
+                         const float* global_k, const float* global_v, int G, const uint8_t* nmask,
+                         int b, int n, int K, int H, int Dh, int M, int kv_heads, float scale, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,6 +226,21 @@ rotate_pool_kernel(const float* __restrict__ Op, const float* __restrict__ D, co
   for (int p = 0; p < P; ++p) dst[p] = (cnt ? acc[p] * inv : 0.f) + (sa ? sa[p] : 0.f);
 }
 
+// sx[node] = 2^j with rowmax[node] * sx < 2^target_exp (1 for all-zero / non-finite rows)
+__global__ void __launch_bounds__(256)
+pow2_scale_kernel(const float* __restrict__ rowmax, int64_t rows, int target_exp, float* __restrict__ sx) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float v = rowmax[r];
+  float s = 1.f;
+  if (v > 0.f && v < 3.0e38f) {
+    int ex;
+    frexpf(v, &ex);
+    s = ldexpf(1.f, max(-100, min(100, target_exp - ex)));
+  }
+  sx[r] = s;
+}
+
 template <int Q>
 static void launch_rg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* D, int64_t E, int64_t tb, int n, int k,
                       int Ci, int cpc, float* X) {
@@ -303,6 +318,14 @@ extern "C" int se3_rowabsmax_fwd(const float* x, int64_t rows, int W, int combin
   using namespace se3;
   SE3_REQUIRE(rows > 0 && W > 0, "se3_rowabsmax_fwd: bad sizes");
   rowabsmax_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(x, rows, W, combine, out);
+  SE3_LAUNCH_OK();
+  return SE3_OK;
+}
+
+extern "C" int se3_pow2_scale_fwd(const float* rowmax, int64_t rows, int target_exp, float* sx, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(rows > 0 && target_exp >= -60 && target_exp <= 60, "se3_pow2_scale_fwd: bad sizes");
+  pow2_scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(rowmax, rows, target_exp, sx);
   SE3_LAUNCH_OK();
   return SE3_OK;
 }

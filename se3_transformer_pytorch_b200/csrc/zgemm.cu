@@ -70,7 +70,7 @@ __device__ __forceinline__ void z_split16(const float (&p)[16], uint32_t (&r)[16
 template <int MODE, int N, int CSZ>
 __global__ void __launch_bounds__(kZThreads, 1)
 zgemm_kernel(const __grid_constant__ ZParams prm) {
-  static_assert(MODE == 1 || ((MODE == 2 || MODE == 3) && N == 128), "MODE 2 / 3 use two / three N = 128 accumulators");
+  static_assert(MODE == 1 || ((MODE == 2 || MODE == 3 || MODE == 4) && N == 128), "MODE 2 / 3 use two / three N = 128 accumulators");
   constexpr int DCOLS = (MODE == 3) ? 384 : (MODE == 2) ? 256 : N;   // accumulator columns in use
   constexpr int ACC = (MODE == 3) ? 128 : DCOLS / 2;      // fp32 partial sums per drain thread (MODE 3: 64 of out'[+], 64 of out'[-])
   constexpr int ASLOT = (MODE == 2) ? 128 : 64;           // TMEM columns of one A stage
@@ -165,7 +165,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         const uint32_t wb = sW + wslot * kStageBytes;
         const bool last_of_blk = (s + 1 == S) || (s + 1 == blk_start + FS);
         if (elect_one()) {
-          if (MODE == 1) {
+          if (MODE == 1 || MODE == 4) {
             uint32_t accum = (s == blk_start) ? 0u : 1u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -225,7 +225,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
     const int64_t eg = mt * SE3_TILE_E + el;
     const bool live = eg < prm.E;
-    const float sxe = live ? prm.sx[eg] : 1.f;
+    const float sxe = (live && MODE != 4) ? prm.sx[eg] : 1.f;
 
     float acc[ACC];
 #pragma unroll
@@ -281,6 +281,59 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       ++flushed;
     };
 
+    if (MODE == 4) {
+      // ---- LinearSE3 (reference S:78-95): rows = (node, m) of x [nodes, D, M], A[row, d] = x[node, d, m] read in place (stride
+      // M), chunk c of stage s = input channels 64 s + 16 c .. +15; out[node, o, m] (+ residual) in the reference layout
+      const ZSeg& z = prm.seg[0];
+      const int M = z.ncomp, D = z.Ci;
+      const int64_t node = live ? eg / M : 0;
+      const int m = live ? (int)(eg - node * M) : 0;
+      const float sc = live ? prm.sx[node] : 1.f;
+      const float* xrow = z.X + ((size_t)node * D) * M + m;
+      float xa[32], xb[32];
+      auto ldhalf = [&](int st, int half, float (&dst)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = live ? __ldg(xrow + (size_t)(st * 64 + half * 32 + j) * M) : 0.f;
+      };
+      auto gen2 = [&](const float (&src)[32], uint32_t a0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = src[c * 16 + j] * sc;
+          uint32_t r[16];
+          z_split16(p, r);
+          tmem_st16(a0 + (uint32_t)(c * 16), r);
+        }
+      };
+      int s = h;
+      if (s < S) ldhalf(s, 0, xa);
+      for (; s < S; s += 2) {
+        ldhalf(s, 1, xb);
+        while (flushed < n_blk && min((flushed + 1) * FS, S) - 1 <= s - AS) drain();
+        const int aslot = s % AS;
+        mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(s / AS) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT);
+        gen2(xa, a0);
+        if (s + 2 < S) ldhalf(s + 2, 0, xa);
+        gen2(xb, a0 + 32u);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
+      }
+      while (flushed < n_blk) drain();
+      if (active && live) {
+        const float inv = 1.f / sc;
+        const int64_t Eo = prm.out_es;                            // output channels of the layer
+        const size_t o0 = (size_t)nt * N + h * ACC;
+        float* dst = prm.out + ((size_t)node * Eo + o0) * M + m;
+        const float* res = z.U ? z.U + ((size_t)node * Eo + o0) * M + m : nullptr;
+#pragma unroll
+        for (int j = 0; j < ACC; ++j) dst[(size_t)j * M] = acc[j] * inv + (res ? __ldg(res + (size_t)j * M) : 0.f);
+      }
+    } else {
     // position of this warp's next stage: (segment, local stage)
     int seg = 0, sl = h;
     while (seg < prm.n_seg && sl >= prm.seg[seg].n_stage) { sl -= prm.seg[seg].n_stage; ++seg; }
@@ -406,6 +459,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
           *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
       }
     }
+    }   // MODE != 4
   }
   tc_fence_before();
   __syncthreads();
@@ -478,7 +532,7 @@ static int z_env_int(const char* name, int dflt) {
 
 extern "C" int se3_zgemm_tile_n(int Co, int mode) {
   if (Co <= 0 || Co % 128 != 0) return -1;
-  if (mode == 2 || mode == 3) return 128;
+  if (mode == 2 || mode == 3 || mode == 4) return 128;
   if (mode != 1) return -1;
   return (Co % 256 == 0) ? 256 : 128;
 }
@@ -506,11 +560,45 @@ extern "C" int se3_zgemm_pack(const float* Fp, int Kp, int col0, int Co, int CiF
   return SE3_OK;
 }
 
+// LinearSE3 on the tensor cores (reference S:78-95): out[node, o, m] = sum_d x[node, d, m] W[d, o] (+ res[node, o, m]) with the A
+// operand read in place from the reference layout (row = (node, m), stride M), split to fp16 hi / lo on the fly; the same
+// pipeline as se3_zgemm_fwd (MODE 4: one N = 128 accumulator, fp32 drain).  w_img = se3_zgemm_pack(W^T viewed [Eo * D/16, 16],
+// Kp 16, col0 0, Co Eo, CiF D/16, mode 4).  sx [nodes]: power-of-two scale per node (se3_node_scale_fwd).
+extern "C" int se3_linear_tc_fwd(const float* x, const void* w_img, const float* res, const float* sx, int64_t nodes, int D, int Eo,
+                                 int M, float* out, void* stream) {
+  using namespace se3;
+  SE3_REQUIRE(nodes > 0 && M >= 1 && M <= 11, "se3_linear_tc_fwd: bad sizes");
+  SE3_REQUIRE(D > 0 && D % 64 == 0 && Eo > 0 && Eo % 128 == 0, "se3_linear_tc_fwd: D=%d must be a multiple of 64 and Eo=%d of 128", D, Eo);
+  SE3_REQUIRE(x != nullptr && w_img != nullptr && sx != nullptr && out != nullptr, "se3_linear_tc_fwd: null pointer");
+  ZParams prm;
+  prm.n_seg = 1;
+  prm.seg[0].U = res;
+  prm.seg[0].X = x;
+  prm.seg[0].Ci = D;
+  prm.seg[0].ncomp = M;
+  prm.seg[0].cplus = prm.seg[0].cminus = 0;
+  prm.seg[0].n_stage = D / 64;
+  prm.seg[0].pad = 0;
+  prm.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  prm.sx = sx;
+  prm.out = out;
+  prm.E = nodes * M;
+  prm.out_es = Eo;
+  prm.comp_off[0] = prm.comp_off[1] = 0;
+  prm.n_mt = (int)ceil_div(prm.E, SE3_TILE_E);
+  prm.n_nt = Eo / 128;
+  prm.S = D / 64;
+  prm.flush_stages = std::max(1, z_env_int("SE3B200_Z_FLUSH", 8));
+  const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
+  cudaStream_t s = as_stream(stream);
+  return csz == 1 ? launch_z<4, 128, 1>(prm, s) : launch_z<4, 128, 2>(prm, s);
+}
+
 extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img, const float* sx, int64_t E, int Co, int mode,
                              float* out, int64_t out_edge_stride, int comp_off0, int comp_off1, int flush_stages, void* stream) {
   using namespace se3;
   const int N = se3_zgemm_tile_n(Co, mode);
-  SE3_REQUIRE(N > 0, "se3_zgemm_fwd: Co=%d must be a multiple of 128 and mode 1, 2 or 3 (got %d)", Co, mode);
+  SE3_REQUIRE(N > 0 && mode != 4, "se3_zgemm_fwd: Co=%d must be a multiple of 128 and mode 1, 2 or 3 (got %d)", Co, mode);
   SE3_REQUIRE(E > 0 && n_seg >= 1 && n_seg <= kZMaxSeg, "se3_zgemm_fwd: bad sizes (1..%d segments)", kZMaxSeg);
   SE3_REQUIRE(segs != nullptr && w_img != nullptr && sx != nullptr && out != nullptr, "se3_zgemm_fwd: null pointer");
   SE3_REQUIRE(out_edge_stride >= Co && out_edge_stride % 4 == 0 && comp_off0 % 4 == 0 && comp_off1 % 4 == 0 &&

@@ -82,20 +82,40 @@ def residual_add(x, res):
 
 
 class LinearSE3(nn.Module):
-    """Per-degree channel mix (reference S:78-95): a plain GEMM, left to cuBLAS."""
+    """Per-degree channel mix (reference S:78-95).  Widths the tensor-core kernel takes (C_in % 64 == 0, C_out % 128 == 0) run
+    on se3_linear_tc_fwd: the A operand is read in place from the reference layout, split to fp16 hi / lo on the fly (fp32
+    parity), an optional residual is added in the epilogue; other widths are a plain cuBLAS GEMM."""
 
     def __init__(self, fiber_in, fiber_out):
         super().__init__()
         self.weights = nn.ParameterDict()
         for degree, dim_in, dim_out in fiber_in.shared(fiber_out):
             self.weights[str(degree)] = nn.Parameter(torch.randn(dim_in, dim_out) / sqrt(dim_in))
+        self._images = {}
 
-    def forward(self, x):
+    def image(self, degree):
+        w = self.weights[degree]
+        ver = (w._version, w.data_ptr())
+        hit = self._images.get(degree)
+        if hit is None or hit[0] != ver:
+            ok = float(w.detach().abs().max()) < 6.0e4              # fp16 range of the hi / lo split
+            hit = (ver, ops.linear_image(w) if ok else None)
+            self._images[degree] = hit
+        return hit[1]
+
+    def forward(self, x, residual=None):
         out = {}
         for degree, w in self.weights.items():
             t = x[degree]                                            # [b, n, d, m]
-            out[degree] = torch.matmul(t.transpose(-1, -2), w).transpose(-1, -2).contiguous()
-        return out
+            res = residual.get(degree) if residual is not None else None
+            if t.is_cuda and t.dtype == torch.float32 and not torch.is_grad_enabled() and ops.linear_supported(w.shape[0], w.shape[1], t.device):
+                img = self.image(degree)
+                if img is not None:
+                    out[degree] = ops.linear_tc(t, img, w.shape[1], res=res)
+                    continue
+            y = torch.matmul(t.transpose(-1, -2), w).transpose(-1, -2).contiguous()
+            out[degree] = y if res is None else y + res
+        return out                                                   # (degrees only in `residual` are dropped, as ResidualSE3 S:67-76)
 
 
 class NormSE3(nn.Module):
@@ -436,6 +456,17 @@ class Geometry:
             self._dmax = float(rel_dist.max())          # the one host synchronisation of the plan lookup, once per forward
         return self._dmax
 
+    def to_global(self, akv):
+        """AlignedKV -> [b, n, k, C, 2lo+1] in the global frame (the rotate-back the attention kernel otherwise fuses)."""
+        if not isinstance(akv, AlignedKV):
+            return akv
+        b, n, k, P, C = akv.t.shape
+        E = b * n * k
+        out = torch.empty((E, C, P), dtype=torch.float32, device=akv.t.device)
+        ops.fold_basis(akv.t.reshape(1, E, P, C), self.frames().D[akv.lo].reshape(-1), E, C, P, P, 1, out, accumulate=False,
+                       component_major=True, name='rotate_back')
+        return out.view(b, n, k, C, P)
+
     def frames(self):
         """Per-edge Wigner matrices D_l(R_e) (se3_frames_fwd, float64 arithmetic on the device; SE3B200_HOST_FRAMES=1: the
         float64 torch restatement in aligned.py)."""
@@ -456,11 +487,20 @@ def check_lowrank_stats(checks):
     return [conv for (conv, _, _), w in zip(checks, worst.tolist()) if not (w <= conv.LR_RUNTIME_TOL)]
 
 
+class AlignedKV:
+    """A ConvSE3 output of degree lo >= 1 still in the edge-aligned frame: t [b, n, k, 2lo+1, C], component
+    major, out[e, c, :] = D_lo(e) t[e, :, c].  AttentionSE3 hands it to the attention kernel, which rotates on the fly;
+    Geometry.to_global() materialises the reference-layout tensor [b, n, k, C, 2lo+1]."""
+
+    def __init__(self, t, lo):
+        self.t, self.lo = t, lo
+
+
 class LowRankPlanMiss(RuntimeError):
     """The radial trunk outputs of a forward left the cached low-rank subspace (distances beyond the plan's range)."""
 
 
-def conv_forward(convs, inp, edge_info, rel_dist, basis):
+def conv_forward(convs, inp, edge_info, rel_dist, basis, keep_aligned=False):
     """Evaluate one or more ConvSE3 that share input features, graph and fibers (to_k / to_v of an attention block)
     in a single sweep: the T blocks (gather x basis) are built once per (degree pair, edge chunk) and consumed by every
     convolution's fused pairwise kernel."""
@@ -559,6 +599,10 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                 st['pooled'] = {do: torch.empty((b * n, mo, to_order(do)), dtype=torch.float32, device=dev) for do, mo in conv.fiber_out}
                 st['self'] = conv.self_interact(inp) if conv.self_interaction else {}
         nmask_flat = None if nmask is None else nmask.reshape(-1)
+        for st in z_states:
+            if keep_aligned and 'pooled' not in st:      # the consumer (attention) rotates back on the fly: keep out' itself
+                st['aligned_out'] = {do: torch.empty((E, to_order(do), mo), dtype=torch.float32, device=dev)
+                                     for do, mo in st['conv'].fiber_out if do > 0}
         for t0 in range(0, n_tiles, tpc):
             tc = min(tpc, n_tiles - t0)
             e0 = t0 * ops.TILE_E
@@ -571,6 +615,10 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                     full = all((do, m) in st['z'] for m in range(do + 1))
                     if do == 0 and 'pooled' not in st:
                         Op = st['outs'][0][e0:e0 + ec]                   # [ec, mo, 1] is [ec, 1, mo]
+                    elif do in st.get('aligned_out', {}):
+                        Op = st['aligned_out'][do][e0:e0 + ec]
+                        if not full:
+                            Op.zero_()
                     else:
                         Op = (torch.empty if full else torch.zeros)((ec, P, mo), dtype=torch.float32, device=dev)
                     for m in range(do + 1):
@@ -590,6 +638,8 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
                         ops.rotate_pool(Op, frames.D[do][e0:e0 + ec] if do > 0 else None, None if nmask_flat is None else nmask_flat[e0:e0 + ec],
                                         None if sa is None else sa.reshape(b * n, mo, P)[e0 // k:(e0 + ec) // k], ec // k, k, mo, do,
                                         st['pooled'][do][e0 // k:(e0 + ec) // k])
+                    elif do in st.get('aligned_out', {}):
+                        pass                            # stays in the edge frame; rotated inside the attention kernel
                     elif do > 0:                        # back to the global frame: out = D_lo out'
                         ops.fold_basis(Op.view(1, ec, P, mo), frames.D[do][e0:e0 + ec].reshape(-1), ec, mo, P, P, 1,
                                        st['outs'][do][e0:e0 + ec], accumulate=False, component_major=True, name='rotate_back')
@@ -686,6 +736,9 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis):
             results.append({str(do): st['pooled'][do].view(b, n, mo, to_order(do)) for do, mo in conv.fiber_out})
             continue
         for do, mo in conv.fiber_out:
+            if do in st.get('aligned_out', {}):
+                outputs[str(do)] = AlignedKV(st['aligned_out'][do].view(b, n, k, to_order(do), mo), do)
+                continue
             o = st['outs'][do].view(b, n, k, mo, to_order(do))
             if conv.pool:
                 o = ops.pool(o, nmask)
@@ -706,8 +759,8 @@ class FeedForwardSE3(nn.Module):
         self.nonlin = NormSE3(hidden)
         self.project_out = LinearSE3(hidden, fiber)
 
-    def forward(self, x):
-        return self.project_out(self.nonlin(self.project_in(x)))
+    def forward(self, x, residual=None):
+        return self.project_out(self.nonlin(self.project_in(x)), residual=residual)
 
 
 class FeedForwardBlockSE3(nn.Module):
@@ -719,7 +772,7 @@ class FeedForwardBlockSE3(nn.Module):
         self.feedforward = FeedForwardSE3(fiber)
 
     def forward(self, x):
-        return residual_add(self.feedforward(self.prenorm(x)), x)
+        return self.feedforward(self.prenorm(x), residual=x)          # residual added in the epilogue of project_out
 
 
 class AttentionSE3(nn.Module):
@@ -768,20 +821,22 @@ class AttentionSE3(nn.Module):
             self.to_global_k = LinearSE3(gin, gout)
             self.to_global_v = LinearSE3(gin, gout)
 
-    def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
+    def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None, residual=None):
         forward_only_guard('AttentionSE3', [self], list(features.values()))
         idx, nmask, _ = edge_info
         queries = self.to_q(features)
         k_idx = None
+        geom = basis[2] if isinstance(basis, tuple) and len(basis) > 2 else None
+        fuse = geom is not None and not os.environ.get('SE3B200_NO_ATTN_ROTATE')    # rotate-back fused into the attention kernel
         if self.linear_proj_keys:
-            values = self.to_v(features, edge_info, rel_dist, basis)
+            values = conv_forward([self.to_v], features, edge_info, rel_dist, basis, keep_aligned=fuse)[0]
             keys = self.to_k(features)            # node level; the attention kernel gathers through idx
             k_idx = idx
         elif self.to_k is None:
-            values = self.to_v(features, edge_info, rel_dist, basis)
+            values = conv_forward([self.to_v], features, edge_info, rel_dist, basis, keep_aligned=fuse)[0]
             keys = values
         else:
-            keys, values = conv_forward([self.to_k, self.to_v], features, edge_info, rel_dist, basis)
+            keys, values = conv_forward([self.to_k, self.to_v], features, edge_info, rel_dist, basis, keep_aligned=fuse)
         if self.attend_self:
             self_keys, self_values = self.to_self_k(features), self.to_self_v(features)
         if exists(global_feats):
@@ -817,10 +872,20 @@ class AttentionSE3(nn.Module):
                           null_v=self.null_values[degree].reshape(-1, to_order(int(degree))))
             if exists(global_feats) and degree == '0':
                 kw.update(global_k=global_keys[degree], global_v=global_values[degree])
-            outputs[degree] = ops.attention(queries[degree], keys[degree], values[degree], heads=self.heads, dim_head=self.dim_head,
+            kd, vd = keys[degree], values[degree]
+            if isinstance(vd, AlignedKV) or isinstance(kd, AlignedKV):
+                if isinstance(kd, AlignedKV) and not isinstance(vd, AlignedKV):
+                    kd = geom.to_global(kd)           # (keys and values come from the same dispatch: not reached in practice)
+                if isinstance(vd, AlignedKV):
+                    k_al = isinstance(kd, AlignedKV)
+                    kw.update(D=geom.frames().D[int(degree)], k_aligned=k_al)
+                    kd, vd = (kd.t if k_al else kd), vd.t
+            outputs[degree] = ops.attention(queries[degree], kd, vd, heads=self.heads, dim_head=self.dim_head,
                                             scale=self.scale, nmask=nmask, k_idx=(None if exists(pos_emb) and degree == '0' else k_idx),
                                             kv_heads=1 if self.one_headed else self.heads, **kw)
-        return self.to_out(outputs)
+        if isinstance(self.to_out, LinearSE3):
+            return self.to_out(outputs, residual=residual)             # residual added in the epilogue of to_out
+        return outputs if residual is None else residual_add(outputs, residual)
 
 
 class SinusoidalEmbeddings(nn.Module):
@@ -866,8 +931,7 @@ class AttentionBlockSE3(nn.Module):
         self.prenorm = NormSE3(fiber, gated_scale=norm_gated_scale)
 
     def forward(self, features, edge_info, rel_dist, basis, global_feats=None, pos_emb=None, mask=None):
-        out = self.attn(self.prenorm(features), edge_info, rel_dist, basis, global_feats, pos_emb, mask)
-        return residual_add(out, features)
+        return self.attn(self.prenorm(features), edge_info, rel_dist, basis, global_feats, pos_emb, mask, residual=features)
 
 
 class SequentialSequence(nn.Module):

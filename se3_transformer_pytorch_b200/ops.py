@@ -44,6 +44,8 @@ _SIGNATURES = {
     'se3_frames_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5),
     'se3_rotgather_fwd': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_int64, c_int64, c_void_p, c_void_p]),
     'se3_rotate_pool_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_linear_tc_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'se3_pow2_scale_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'se3_rowabsmax_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'se3_edge_scale_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_zgemm_tile_n': (c_int, [c_int, c_int]),
@@ -52,6 +54,7 @@ _SIGNATURES = {
     'se3_zgemm_fwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     'se3_pool_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     'se3_norm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'se3_attn_aligned_fwd': (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 7 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
     'se3_attn_fwd': (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_int] * 7 + [c_float, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -552,6 +555,48 @@ def edge_scale(feats, idx, max_degree):
     return sx
 
 
+def linear_supported(D, Eo, device):
+    """Shapes the tensor-core LinearSE3 kernel takes."""
+    if os.environ.get('SE3B200_NO_LINEAR_TC') or os.environ.get('SE3B200_FORCE_SIMT'):
+        return False
+    return D % 64 == 0 and Eo % 128 == 0 and torch.cuda.get_device_capability(device)[0] == 10
+
+
+def linear_image(W):
+    """W [D, Eo] fp32 (LinearSE3.weights[degree]) -> tensor-core operand image of W^T for linear_tc."""
+    _require_cuda(W)
+    D, Eo = W.shape
+    Fp = _f32(W.detach().t()).contiguous().reshape(Eo * (D // 16), 16)
+    nbytes = lib().se3_zgemm_image_bytes(Eo, 4, D // 64)
+    if nbytes < 0:
+        raise RuntimeError(f'linear_image: unsupported shape D={D} Eo={Eo}')
+    img = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    with torch.cuda.device(W.device):
+        _check(lib().se3_zgemm_pack(_p(Fp), 16, 0, Eo, D // 16, 4, D // 64, 0, _p(img), _stream()))
+    return img
+
+
+def linear_tc(x, img, Eo, res=None):
+    """LinearSE3 on the tensor cores: x [b,n,D,M] (reference layout, read in place) -> [b,n,Eo,M] (+ res)."""
+    _require_cuda(x, img, res)
+    x = _f32(x)
+    b, n, D, M = x.shape
+    nodes = b * n
+    out = torch.empty((b, n, Eo, M), dtype=torch.float32, device=x.device)
+    if res is not None:
+        res = _f32(res)
+        assert res.shape == out.shape
+    with torch.cuda.device(x.device):
+        rowmax = torch.empty(nodes, dtype=torch.float32, device=x.device)
+        sx = torch.empty(nodes, dtype=torch.float32, device=x.device)
+        _check(lib().se3_rowabsmax_fwd(_p(x), nodes, D * M, 0, _p(rowmax), _stream()))
+        _check(lib().se3_pow2_scale_fwd(_p(rowmax), nodes, 14, _p(sx), _stream()))
+        nbytes = img.numel() + 4 * (2 * x.numel() + out.numel() * (2 if res is not None else 1))
+        with _timed('linear', flops=2 * nodes * M * D * Eo, nbytes=nbytes, mma=2 * nodes * M * D * Eo * 3, tag=f'linear D{D}E{Eo}M{M}'):
+            _check(lib().se3_linear_tc_fwd(_p(x), _p(img), _p(res), _p(sx), nodes, D, Eo, M, _p(out), _stream()))
+    return out
+
+
 def zgemm_tile_n(Co, mode):
     return lib().se3_zgemm_tile_n(Co, mode)
 
@@ -663,10 +708,12 @@ def pool(x, mask):
 # K5
 # ---------------------------------------------------------------------------------------------------------
 def attention(q, k, v, *, heads, dim_head, scale, nmask=None, k_idx=None, self_k=None, self_v=None, null_k=None, null_v=None,
-              global_k=None, global_v=None, kv_heads=None):
+              global_k=None, global_v=None, kv_heads=None, D=None, k_aligned=False):
     """One degree of AttentionSE3 / OneHeadedKVAttentionSE3 (reference S:476-517, 612-652).
-    q [b,n,H*Dh,M]; k,v [b,n,K,Ckv,M] (k may be node level [b,n,Ckv,M] with k_idx [b,n,K])."""
-    _require_cuda(q, k, v)
+    q [b,n,H*Dh,M]; k,v [b,n,K,Ckv,M] (k may be node level [b,n,Ckv,M] with k_idx [b,n,K]).
+    With D [b*n*K, M, M] (edge frames): v (and k if k_aligned) are the edge-aligned, component-major [b,n,K,M,Ckv] outputs of
+    zgemm and the rotation back to the global frame is fused into the kernel (se3_attn_aligned_fwd)."""
+    _require_cuda(q, k, v, D)
     q, k, v = _f32(q), _f32(k), _f32(v)
     b, n, _, M = q.shape
     K = v.shape[2]
@@ -679,6 +726,14 @@ def attention(q, k, v, *, heads, dim_head, scale, nmask=None, k_idx=None, self_k
     ki = None if k_idx is None else k_idx.contiguous()
     J = K + G + (self_k is not None) + (null_k is not None)
     nbytes = 4 * (2 * q.numel() + 2 * b * n * J * heads * dim_head * M)
+    if D is not None:
+        assert M > 1 and D.is_contiguous() and D.numel() == b * n * K * M * M and v.shape[3] == M
+        nbytes += 4 * D.numel()
+        with torch.cuda.device(q.device), _timed('attention', flops=4 * b * n * J * heads * dim_head * M * (1 + M), nbytes=nbytes):
+            _check(lib().se3_attn_aligned_fwd(_p(q), _p(k), _p(v), _p(D), int(bool(k_aligned)), _p(ki), _p(self_k), _p(self_v), _p(null_k),
+                                              _p(null_v), _p(global_k), _p(global_v), G, _p(nm), b, n, K, heads, dim_head, M, kv_heads,
+                                              float(scale), _p(out), _stream()))
+        return out
     with torch.cuda.device(q.device), _timed('attention', flops=4 * b * n * J * heads * dim_head * M, nbytes=nbytes):
         _check(lib().se3_attn_fwd(_p(q), _p(k), _p(v), _p(ki), _p(self_k), _p(self_v), _p(null_k), _p(null_v), _p(global_k),
                                   _p(global_v), G, _p(nm), b, n, K, heads, dim_head, M, kv_heads, float(scale), _p(out), _stream()))

@@ -33,12 +33,14 @@ def _capture_attention(model, feats, coors, mask):
     attn = model.net.blocks[0][0].attn
     orig_conv, orig_attn_op, orig_knn = M.conv_forward, ops.attention, ops.knn
 
-    def conv_spy(convs, inp, edge_info, rel_dist, basis):
-        outs = orig_conv(convs, inp, edge_info, rel_dist, basis)
+    def conv_spy(convs, inp, edge_info, rel_dist, basis, **kw):
+        outs = orig_conv(convs, inp, edge_info, rel_dist, basis, **kw)
         if len(convs) == 2 and convs[0] is attn.to_k and 'k' not in rec:
             rec['inp'] = {d: t.clone() for d, t in inp.items()}
-            rec['k'] = {d: t.clone() for d, t in outs[0].items()}
-            rec['v'] = {d: t.clone() for d, t in outs[1].items()}
+            # degrees >= 1 stay in the edge-aligned frame for the attention kernel (AlignedKV): to_global() is the same rotate-back
+            rec['fused_rotate'] = any(isinstance(t, M.AlignedKV) for t in outs[0].values())
+            rec['k'] = {d: basis[2].to_global(t).clone() for d, t in outs[0].items()}
+            rec['v'] = {d: basis[2].to_global(t).clone() for d, t in outs[1].items()}
         return outs
 
     def attn_spy(q, k, v, **kw):
@@ -108,7 +110,7 @@ def test_production_path_matches_oracle_at_headline_width(k_nbr, n):
     out, rec = _capture_attention(model, feats, coors, mask)
     kinds = set(rec['kinds'])
     assert kinds & {'zgemm', 'pairwise_lr'}, kinds               # the low-rank tensor-core kernel ran ...
-    assert 'rotate_back' in kinds, kinds                         # ... in edge-aligned frames
+    assert rec['fused_rotate'] and 'rotgather' in kinds, kinds   # ... in edge-aligned frames, rotate-back fused into attention
     assert 'pairwise_tc' not in kinds and 'pairwise_simt' not in kinds, kinds
     rng = np.random.default_rng(0)
     nodes = np.sort(rng.choice(n, size=256 // k_nbr, replace=False))     # 256 edges at full width
@@ -138,7 +140,7 @@ def test_production_path_matches_simt_whole_model():
     finally:
         prof, ops.PROFILE = ops.PROFILE, None
     kinds = {p[0] for p in prof}
-    assert kinds & {'zgemm', 'pairwise_lr'} and 'rotate_back' in kinds, kinds
+    assert kinds & {'zgemm', 'pairwise_lr'} and 'rotgather' in kinds, kinds
     os.environ['SE3B200_FORCE_SIMT'] = '1'
     try:
         for m in model.conv_modules():

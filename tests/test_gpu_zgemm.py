@@ -207,3 +207,97 @@ def test_radial_trunk_u():
         assert abs(float(stats[p, 1]) - float(g_ref[p].abs().max())) < 1e-6
     U2, none = ops.radial_trunk_u(feat, params, V, gmean, ones_col, stats)
     assert none is None and torch.equal(U2, U)
+
+
+@pytest.mark.parametrize('M,Dh,H,K,opts', [
+    (3, 16, 2, 5, dict(self_kv=True)),
+    (7, 64, 8, 16, dict(self_kv=True, mask=True)),
+    (5, 24, 3, 9, dict(self_kv=True, null=True, one_headed=True, mask=True)),
+    (3, 8, 2, 4, dict(self_kv=True, linear_keys=True)),
+    (7, 40, 2, 6, dict(mask=True, all_masked_row=True, self_kv=False)),
+])
+def test_attention_with_fused_rotate_back(M, Dh, H, K, opts):
+    """se3_attn_aligned_fwd (keys / values in the edge frame, rotated inside the kernel) == se3_attn_fwd on the rotated tensors."""
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(M * 100 + K)
+    b, n = 2, 11
+    hk = 1 if opts.get('one_headed') else H
+    Ckv = hk * Dh
+    rn = lambda *s: torch.randn(*s, generator=g).to(DEV)
+    q = rn(b, n, H * Dh, M)
+    kp, vp = rn(b, n, K, M, Ckv), rn(b, n, K, M, Ckv)              # aligned, component major
+    Dm, _ = torch.linalg.qr(torch.randn(b * n * K, M, M, generator=g))
+    Dm = Dm.to(DEV).contiguous()
+    rot = lambda t: torch.einsum('epn,enc->ecp', Dm.double(), t.reshape(-1, M, Ckv).double()).float().reshape(b, n, K, Ckv, M)
+    kw = dict(heads=H, dim_head=Dh, scale=Dh ** -0.5, kv_heads=hk)
+    if opts.get('self_kv'):
+        kw.update(self_k=rn(b, n, Ckv, M), self_v=rn(b, n, Ckv, M))
+    if opts.get('null'):
+        kw.update(null_k=rn(Ckv, M), null_v=rn(Ckv, M))
+    if opts.get('mask'):
+        m = torch.rand(b, n, K, generator=g) > 0.3
+        if opts.get('all_masked_row'):
+            m[0, 0] = False
+        kw.update(nmask=m.to(DEV))
+    if opts.get('linear_keys'):
+        k_node = rn(b, n, Ckv, M)
+        idx = torch.randint(0, n, (b, n, K), generator=g).to(DEV)
+        ref = ops.attention(q, k_node, rot(vp), k_idx=idx, **kw)
+        out = ops.attention(q, k_node, vp, k_idx=idx, D=Dm, k_aligned=False, **kw)
+    else:
+        ref = ops.attention(q, rot(kp), rot(vp), **kw)
+        out = ops.attention(q, kp, vp, D=Dm, k_aligned=True, **kw)
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-6
+
+
+@pytest.mark.parametrize('lo,K,Co,masked,self_add', [(0, 8, 128, True, True), (1, 5, 96, True, False), (3, 16, 256, True, True), (2, 40, 300, False, True)])
+def test_rotate_pool(lo, K, Co, masked, self_add):
+    """Fused rotate-back + masked mean over the neighbours + self-interaction (S:256-266, utils.py:72-80)."""
+    from se3_transformer_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(lo)
+    nodes, P = 23, 2 * lo + 1
+    Op = torch.randn(nodes * K, P, Co, generator=g).to(DEV)
+    D = torch.randn(nodes * K, P, P, generator=g).to(DEV) if lo else None
+    mask = (torch.rand(nodes * K, generator=g) > 0.4).to(DEV) if masked else None
+    if masked:
+        mask[:K] = False                                           # a node with no valid neighbour -> zero (+ self term)
+    sa = torch.randn(nodes, Co, P, generator=g).to(DEV) if self_add else None
+    out = torch.empty(nodes, Co, P, device=DEV)
+    ops.rotate_pool(Op, D, mask, sa, nodes, K, Co, lo, out)
+    rot = Op.double().transpose(1, 2) if D is None else torch.einsum('epn,enc->ecp', D.double(), Op.double())       # [E, Co, P]
+    rot = rot.reshape(nodes, K, Co, P)
+    if mask is None:
+        ref = rot.mean(1)
+    else:
+        mk = mask.reshape(nodes, K, 1, 1).double()
+        cnt = mk.sum(1)
+        ref = (rot * mk).sum(1) / cnt.clamp(min=1.0)
+        ref = torch.where(cnt == 0, torch.zeros_like(ref), ref)
+    if sa is not None:
+        ref = ref + sa.double()
+    assert float((out.double() - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('D,Eo,M,nodes,with_res', [(64, 128, 1, 37, False), (512, 512, 7, 50, True), (2048, 512, 3, 33, True),
+                                                   (512, 2048, 5, 29, False), (128, 256, 1, 300, True)])
+def test_linear_tc_matches_fp64(D, Eo, M, nodes, with_res):
+    """LinearSE3 on the tensor cores (reference S:78-95, A operand read in place from [b,n,D,M]) vs float64, also with the
+    fused residual and with features of very different magnitude per node (the per-node power-of-two scale)."""
+    from se3_transformer_pytorch_b200 import ops
+    if not ops.linear_supported(D, Eo, DEV):
+        pytest.skip('needs sm_100')
+    g = torch.Generator().manual_seed(D + M)
+    x = torch.randn(1, nodes, D, M, generator=g)
+    x = x * torch.logspace(-6, 4, nodes).view(1, nodes, 1, 1)          # per-node magnitudes 1e-6 .. 1e4
+    x[0, 3] = 0.0
+    x = x.to(DEV)
+    W = (torch.randn(D, Eo, generator=g) / D ** 0.5).to(DEV)
+    res = torch.randn(1, nodes, Eo, M, generator=g).to(DEV) * x.abs().amax(dim=(2, 3), keepdim=True) if with_res else None
+    out = ops.linear_tc(x, ops.linear_image(W), Eo, res=res)
+    ref = torch.einsum('bndm,de->bnem', x.double(), W.double())
+    if res is not None:
+        ref = ref + res.double()
+    # relative to each node's own output scale (rows differ by 10 orders of magnitude)
+    scale = ref.abs().amax(dim=(2, 3), keepdim=True).clamp(min=1e-30)
+    assert float(((out.double() - ref).abs() / scale).max()) < 3e-6
+    assert float(out[0, 3].abs().max()) == 0.0 or with_res
