@@ -67,6 +67,24 @@ __device__ __forceinline__ void z_split16(const float (&p)[16], uint32_t (&r)[16
   }
 }
 
+// Z = U * y for 16 radial coordinates and one scalar y, as fp16 pairs hi (r[0..7]) + lo (r[8..15]) with hi + lo = U y to ~2^-22,
+// entirely in packed half arithmetic (4 instructions per pair of values, no conversions): with U = Uh + Ul, y = yh + yl,
+//     hi = fl(Uh yh);   e = fma(Uh, yh, -hi)  (the rounding error of that product, exact: TwoProduct);   lo = Uh yl + (Ul yh + e)
+// (Ul yl ~ 2^-22 is dropped).  Uh / Ul: the segment's radial coordinates, split once per segment.
+__device__ __forceinline__ void z_outer16(const __half2 (&Uh)[8], const __half2 (&Ul)[8], float y, uint32_t (&r)[16]) {
+  const __half yh1 = __float2half_rn(y);
+  const __half yl1 = __float2half_rn(y - __half2float(yh1));
+  const __half2 yh = __half2half2(yh1), yl = __half2half2(yl1);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const __half2 hi = __hmul2(Uh[c], yh);
+    const __half2 e = __hfma2(Uh[c], yh, __hneg2(hi));
+    const __half2 lo = __hfma2(Uh[c], yl, __hfma2(Ul[c], yh, e));
+    r[c] = *reinterpret_cast<const uint32_t*>(&hi);
+    r[8 + c] = *reinterpret_cast<const uint32_t*>(&lo);
+  }
+}
+
 template <int MODE, int N, int CSZ>
 __global__ void __launch_bounds__(kZThreads, 1)
 zgemm_kernel(const __grid_constant__ ZParams prm) {
@@ -339,7 +357,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
     while (seg < prm.n_seg && sl >= prm.seg[seg].n_stage) { sl -= prm.seg[seg].n_stage; ++seg; }
     int s = h;                                 // global stage index
     int cur_seg = -1;
-    float us[16];
+    __half2 Uh[8], Ul[8];                      // the segment's radial coordinates U[e, 0..15], split hi / lo
     const float* Xp = nullptr;                 // component row(s) of this thread inside the current segment's X
     int xstride = 0, cp = 0, cm = 0, Ci = 0;
 
@@ -388,7 +406,11 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const float4 u4 = live ? __ldg(urow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-          us[4 * v + 0] = u4.x * sxe; us[4 * v + 1] = u4.y * sxe; us[4 * v + 2] = u4.z * sxe; us[4 * v + 3] = u4.w * sxe;
+          const __half2 h0 = __floats2half2_rn(u4.x, u4.y), h1 = __floats2half2_rn(u4.z, u4.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          Uh[2 * v] = h0; Uh[2 * v + 1] = h1;
+          Ul[2 * v] = __floats2half2_rn(u4.x - f0.x, u4.y - f0.y);
+          Ul[2 * v + 1] = __floats2half2_rn(u4.z - f1.x, u4.w - f1.y);
         }
         cur_seg = seg;
       }
@@ -401,24 +423,16 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       if (MODE == 1 || MODE == 3) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float p[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[c];
           uint32_t r[16];
-          z_split16(p, r);
+          z_outer16(Uh, Ul, xv[c] * sxe, r);
           tmem_st16(a0 + (uint32_t)(c * 16), r);
         }
       } else {
 #pragma unroll
         for (int il = 0; il < 2; ++il) {
-          float p[16];
           uint32_t rP[16], rM[16], nM[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[2 * il];
-          z_split16(p, rP);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) p[j] = us[j] * xv[2 * il + 1];
-          z_split16(p, rM);
+          z_outer16(Uh, Ul, xv[2 * il] * sxe, rP);
+          z_outer16(Uh, Ul, xv[2 * il + 1] * sxe, rM);
 #pragma unroll
           for (int j = 0; j < 16; ++j) nM[j] = rM[j] ^ 0x80008000u;
           // component +m: (f = a: U x+), (f = b: -U x-);   component -m: (f = a: U x-), (f = b: U x+)
