@@ -299,5 +299,6 @@ def test_linear_tc_matches_fp64(D, Eo, M, nodes, with_res):
         ref = ref + res.double()
     # relative to each node's own output scale (rows differ by 10 orders of magnitude)
     scale = ref.abs().amax(dim=(2, 3), keepdim=True).clamp(min=1e-30)
-    assert float(((out.double() - ref).abs() / scale).max()) < 3e-6
+    # 3-pass fp16 split (~2^-21 per product) + fp32 partial sums: a few 1e-6 of the row's scale
+    assert float(((out.double() - ref).abs() / scale).max()) < 6e-6
     assert float(out[0, 3].abs().max()) == 0.0 or with_res
