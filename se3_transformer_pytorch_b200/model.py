@@ -481,10 +481,15 @@ class Geometry:
 def check_lowrank_stats(checks):
     """checks: [(ConvSE3, stats [pairs, 2] = (max |g - U V^T|, max |g|) of one forward)].  ONE host synchronisation for all of
     them; returns the ConvSE3 modules whose cached radial basis does not cover this forward's distances."""
+    global LAST_PLAN_RESIDUAL
     if not checks:
         return []
     worst = torch.stack([torch.where(have, st[:, 0] / st[:, 1].clamp(min=1e-30), torch.zeros_like(st[:, 0])).max() for _, st, have in checks]).cpu()
+    LAST_PLAN_RESIDUAL = float(worst.max())      # diagnostics / tests: how close the last checked forward came to the guard
     return [conv for (conv, _, _), w in zip(checks, worst.tolist()) if not (w <= conv.LR_RUNTIME_TOL)]
+
+
+LAST_PLAN_RESIDUAL = None
 
 
 class AlignedKV:

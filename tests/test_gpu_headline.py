@@ -151,3 +151,57 @@ def test_production_path_matches_simt_whole_model():
     for d in ('0', '1'):
         err = rel_err(out[d].cpu().numpy(), ref[d].cpu().numpy())
         assert err < TOL, f'degree {d}: {err:.3e}'
+
+
+def test_plan_guard_bounds_the_output_error():
+    """The run-time guard of the low-rank plan is on the radial trunk outputs (max |g - gmean - U V^T| <= 1e-5 max |g| on the edges
+    of the forward), the contract on the outputs (1e-4).  Drive a model with released masters (plan built for distances <= 2) with
+    growing point clouds until the guard rejects the input: every ACCEPTED forward -- including the ones whose residual sits just
+    below the guard -- must match the direct K = 128 kernels of an identical model within 1e-4, and the first rejected one must
+    raise LowRankPlanMiss instead of returning a degraded result.  The (residual, output error) pairs are recorded."""
+    import json
+    from se3_transformer_pytorch_b200 import SE3Transformer, ops, model as M
+    if not ops.tc_supported(DEV, 128, 1):
+        pytest.skip('needs sm_100')
+    ctor = dict(dim=128, heads=2, dim_head=64, depth=1, num_degrees=3, output_degrees=2, num_neighbors=8)
+    torch.manual_seed(5)
+    with torch.device(DEV):
+        direct = SE3Transformer(**ctor).eval()
+    torch.manual_seed(5)
+    with torch.device(DEV):
+        planned = SE3Transformer(**ctor).eval()
+    os.environ['SE3B200_LOWRANK_MIN_EDGES'] = '0'
+    try:
+        planned.pack_weights(free_master=True, max_distance=2.0)
+    finally:
+        del os.environ['SE3B200_LOWRANK_MIN_EDGES']
+    g = torch.Generator().manual_seed(9)
+    n = 96
+    feats = torch.randn(1, n, 128, generator=g).to(DEV)
+    base = torch.randn(1, n, 3, generator=g).to(DEV) * 0.25
+    mask = torch.ones(1, n, dtype=torch.bool, device=DEV)
+    rows, accepted, rejected = [], 0, 0
+    for scale in (1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 8.0, 10.0, 14.0, 20.0, 40.0):
+        coors = base * scale
+        os.environ['SE3B200_NO_LOWRANK'] = '1'
+        try:
+            ref = direct(feats, coors, mask)
+        finally:
+            del os.environ['SE3B200_NO_LOWRANK']
+        try:
+            out = planned(feats, coors, mask)
+        except M.LowRankPlanMiss:
+            rejected += 1
+            rows.append(dict(scale=scale, residual=M.LAST_PLAN_RESIDUAL, accepted=False))
+            continue
+        accepted += 1
+        err = max(rel_err(out[d].cpu().numpy(), ref[d].cpu().numpy()) for d in ('0', '1'))
+        rows.append(dict(scale=scale, residual=M.LAST_PLAN_RESIDUAL, accepted=True, output_rel_err=err))
+        assert M.LAST_PLAN_RESIDUAL <= M.ConvSE3.LR_RUNTIME_TOL
+        assert err < TOL, f'scale {scale}: residual {M.LAST_PLAN_RESIDUAL:.2e} was accepted but the output is off by {err:.2e}'
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/plan_guard.jsonl', 'w') as f:
+        for r in rows:
+            f.write(json.dumps(r) + '\n')
+    print(rows)
+    assert accepted >= 2 and rejected >= 1, rows
