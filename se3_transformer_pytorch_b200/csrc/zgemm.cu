@@ -130,7 +130,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       mbar_init(bar_w_empty + 8 * s, CSZ);
     }
     for (int s = 0; s < AS; ++s) {
-      mbar_init(bar_a_full + 8 * s, MODE == 3 ? 8 : 4);       // MODE 3: both warps of a lane quarter fill every stage
+      mbar_init(bar_a_full + 8 * s, 4);
       mbar_init(bar_a_empty + 8 * s, 1);
     }
     mbar_init(bar_d_full, 1);
@@ -196,17 +196,22 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
               accum = 1u;
             }
           } else if (MODE == 3) {
-            const uint32_t d = tmem_base + (uint32_t)((s % 3) * 128);       // S1 / S2 / S3: the weight set of this stage
-            uint32_t accum = (s - blk_start < 3) ? 0u : 1u;                 // first stage of its set in this block
+            // chunk c of stage s belongs to weight set (s + c) % 3 (every segment has a multiple of 3 stages); pass-major order:
+            // consecutive MMAs hit S1, S2, S3, S1' in turn
+            const int blk_first = (s == blk_start);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
-              const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
-              const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
-              tc_mma_f16_ts(d, a_hi, b_hi, kIdesc, accum);
-              tc_mma_f16_ts(d, a_hi + 8, b_hi, kIdesc, 1u);
-              tc_mma_f16_ts(d, a_hi, b_lo, kIdesc, 1u);
-              accum = 1u;
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int ty = (s + c) % 3;
+                const uint32_t d = tmem_base + (uint32_t)(ty * 128);
+                const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
+                const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
+                const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+                // first MMA into an accumulator in this block overwrites it: pass 0 of chunks 0..2 of the block's first stage
+                const uint32_t accum = (blk_first && pass == 0 && c < 3) ? 0u : 1u;
+                tc_mma_f16_ts(d, pass == 1 ? a_hi + 8 : a_hi, pass == 2 ? b_lo : b_hi, kIdesc, accum);
+              }
             }
           } else {
 #pragma unroll
@@ -255,10 +260,8 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       mbar_wait(bar_d_full, (uint32_t)flushed & 1u);
       tc_fence_after();
       if (MODE == 3) {
-        // channels h*64 .. h*64+63 of the three sets: out'[+] += S1 - S3, out'[-] += S1 + S2.  A set that received no stage in
-        // this block (a block of fewer than 3 stages) holds stale data: skip it.
-        const int blk0 = flushed * FS, nst = min(FS, S - blk0);
-        const bool has1 = nst > (((0 - blk0) % 3 + 3) % 3), has2 = nst > (((1 - blk0) % 3 + 3) % 3), has3 = nst > (((2 - blk0) % 3 + 3) % 3);
+        // channels h*64 .. h*64+63 of the three sets: out'[+] += S1 - S3, out'[-] += S1 + S2
+        constexpr bool has1 = true, has2 = true, has3 = true;      // every stage feeds all three sets
         const uint32_t c0 = tmem_base + t_lane + (uint32_t)(h * 64);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -351,85 +354,6 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
 #pragma unroll
         for (int j = 0; j < ACC; ++j) dst[(size_t)j * M] = acc[j] * inv + (res ? __ldg(res + (size_t)j * M) : 0.f);
       }
-    } else if (MODE == 3) {
-      // ---- cooperative generation: with three accumulators there is room for only two A stages, and a stage is only 768
-      // tensor-pipe cycles long, so the hand-off chain (slot free -> generate -> tcgen05.st -> arrive -> MMA issue) must be short:
-      // BOTH warps of a lane quarter fill every stage (warp h the chunks 2h, 2h+1 = input channels 4g+2h, 4g+2h+1 of weight set
-      // t = stage % 3) and form them in registers before waiting for the slot.
-      int seg = 0, sl = 0, cur_seg = -1;
-      __half2 Uh[8], Ul[8];
-      auto load2 = [&](int sg, int stage_local, float (&xp)[2], float (&xm)[2]) {
-        const ZSeg& z = prm.seg[sg];
-        const float* xb = z.X + ((size_t)mt * z.Ci * z.ncomp) * 128 + el;
-        const int ty = stage_local % 3, i0 = (stage_local / 3) * 4 + 2 * h;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int i = i0 + c;
-          xp[c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
-          xm[c] = (i < z.Ci && ty != 0) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
-        }
-      };
-      auto advance = [&](int& sg, int& stl) {
-        ++stl;
-        while (sg < prm.n_seg && stl >= prm.seg[sg].n_stage) { stl -= prm.seg[sg].n_stage; ++sg; }
-      };
-      float xp0[2] = {0.f, 0.f}, xm0[2] = {0.f, 0.f}, xp1[2] = {0.f, 0.f}, xm1[2] = {0.f, 0.f};   // this stage / the next one
-      int seg1 = 0, sl1 = 0;
-      if (seg < prm.n_seg) load2(seg, sl, xp0, xm0);
-      advance(seg1, sl1);
-      if (seg1 < prm.n_seg) load2(seg1, sl1, xp1, xm1);
-      for (int s = 0; s < S; ++s) {
-        int seg2 = seg1, sl2 = sl1;
-        advance(seg2, sl2);
-        float xp2[2] = {0.f, 0.f}, xm2[2] = {0.f, 0.f};
-        if (seg2 < prm.n_seg) load2(seg2, sl2, xp2, xm2);          // two stages ahead
-        if (seg != cur_seg) {
-          const float4* urow = reinterpret_cast<const float4*>(prm.seg[seg].U + (size_t)(live ? eg : 0) * 64);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const float4 u4 = live ? __ldg(urow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const __half2 h0 = __floats2half2_rn(u4.x, u4.y), h1 = __floats2half2_rn(u4.z, u4.w);
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            Uh[2 * v] = h0; Uh[2 * v + 1] = h1;
-            Ul[2 * v] = __floats2half2_rn(u4.x - f0.x, u4.y - f0.y);
-            Ul[2 * v + 1] = __floats2half2_rn(u4.z - f1.x, u4.w - f1.y);
-          }
-          cur_seg = seg;
-        }
-        const int ty = sl % 3;                                     // weight set (a+b, a, b) <-> y = (c, d - c, c + d)
-        uint32_t rz[2][16];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float y = (ty == 0) ? xp0[c] : (ty == 1) ? (xm0[c] - xp0[c]) : (xp0[c] + xm0[c]);
-          z_outer16(Uh, Ul, y * sxe, rz[c]);
-        }
-        while (flushed < n_blk && min((flushed + 1) * FS, S) - 1 <= s - AS) drain();
-        const int aslot = s % AS;
-        mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(s / AS) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT + 2 * h * 16);
-        tmem_st16(a0, rz[0]);
-        tmem_st16(a0 + 16u, rz[1]);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) { xp0[c] = xp1[c]; xm0[c] = xm1[c]; xp1[c] = xp2[c]; xm1[c] = xm2[c]; }
-        seg = seg1; sl = sl1; seg1 = seg2; sl1 = sl2;
-      }
-      while (flushed < n_blk) drain();
-      if (active && live) {
-        const float inv = 1.f / sxe;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float* dst = prm.out + (size_t)eg * prm.out_es + prm.comp_off[c] + (size_t)nt * N + h * 64;
-#pragma unroll
-          for (int j = 0; j < 64; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[c * 64 + j] * inv, acc[c * 64 + j + 1] * inv, acc[c * 64 + j + 2] * inv,
-                                                              acc[c * 64 + j + 3] * inv);
-        }
-      }
     } else {
     // position of this warp's next stage: (segment, local stage)
     int seg = 0, sl = h;
@@ -445,14 +369,14 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       const ZSeg& z = prm.seg[sg];
       const float* xb = z.X + ((size_t)mt * z.Ci * z.ncomp) * 128 + el;
       if (MODE == 3) {
-        const int ty = stage_local % 3, i0 = (stage_local / 3) * 4;
+        // chunk c of the stage = K chunk q = 4 stage + c of the segment: input channel q / 3, weight set q % 3.  Raw loads only:
+        // combining them here would wait for the loads at once and expose the memory latency of every stage (ncu: 14 % of all
+        // stall samples on that FADD); c, d - c, c + d are formed when the stage is generated
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int i = i0 + c;
-          // raw loads only: combining them here would wait for the loads at once and expose the memory latency of every stage
-          // (ncu: 14 % of all stall samples on this FADD); c, d - c, c + d are formed when the stage is generated
+          const int i = (stage_local * 4 + c) / 3;
           xv[c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
-          xv[4 + c] = (i < z.Ci && ty != 0) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
+          xv[4 + c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
         }
       } else if (MODE == 1) {
 #pragma unroll
@@ -493,19 +417,6 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         }
         cur_seg = seg;
       }
-      // MODE 1 / 3: the whole stage is formed in registers BEFORE waiting for its ring slot, so that the hand-off chain
-      // (slot free -> tcgen05.st -> arrive -> MMA issue) carries no arithmetic: with three accumulators MODE 3 has room for only
-      // two A slots, and a stage is only 768 tensor-pipe cycles long
-      uint32_t rz[(MODE == 2) ? 1 : 4][16];
-      if (MODE == 1 || MODE == 3) {
-        const int ty = (MODE == 3) ? sl % 3 : 0;                 // weight set of this stage: (a+b, a, b) <-> y = (c, d - c, c + d)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float y = xv[c];
-          if (MODE == 3) y = (ty == 0) ? xv[c] : (ty == 1) ? (xv[4 + c] - xv[c]) : (xv[c] + xv[4 + c]);
-          z_outer16(Uh, Ul, y * sxe, rz[c]);
-        }
-      }
       // drain every accumulation block that ended at least AS stages ago (the MMA warp cannot run further ahead anyway)
       while (flushed < n_blk && min((flushed + 1) * FS, S) - 1 <= s - AS) drain();
       const int aslot = s % AS;
@@ -514,7 +425,16 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT);
       if (MODE == 1 || MODE == 3) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_st16(a0 + (uint32_t)(c * 16), rz[c]);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[16];
+          float y = xv[c];
+          if (MODE == 3) {
+            const int ty = (sl + c) % 3;                         // weight set (a+b, a, b) <-> y = (c, d - c, c + d)
+            y = (ty == 0) ? xv[c] : (ty == 1) ? (xv[4 + c] - xv[c]) : (xv[c] + xv[4 + c]);
+          }
+          z_outer16(Uh, Ul, y * sxe, r);
+          tmem_st16(a0 + (uint32_t)(c * 16), r);
+        }
       } else {
 #pragma unroll
         for (int il = 0; il < 2; ++il) {
@@ -574,7 +494,8 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
 
 // Weight image of one sub-segment: rows (o, i, f) of Fp (columns [col0, col0+16) of each row) -> stages [stage0, stage0+n) of
 // the launch image.  Chunk c = i*F + f of the segment sits in stage c/4 at K columns [(c%4)*16, +16).
-// gauss != 0 (MODE 3): Fp rows are (o, i, f in {a, b}); stage sl = 3 g + t holds input channels 4g..4g+3 of weight set t = (a+b, a, b).
+// gauss != 0 (MODE 3): Fp rows are (o, i, f in {a, b}); K chunk q = 4 sl + c of the segment = weight set q % 3 of (a+b, a, b) of
+// input channel q / 3.
 __global__ void zpack_kernel(const float* __restrict__ Fp, int Kp, int col0, int Co, int CiF, int N, int S, int stage0, int n_stage,
                              int gauss, uint8_t* __restrict__ img) {
   const int nt = blockIdx.y, sl = blockIdx.x;
@@ -584,7 +505,8 @@ __global__ void zpack_kernel(const float* __restrict__ Fp, int Kp, int col0, int
     const int o = nt * N + r;
     float w = 0.f;
     if (gauss) {
-      const int ty = sl % 3, i = (sl / 3) * 4 + (k >> 4);
+      const int q = sl * 4 + (k >> 4);
+      const int ty = q % 3, i = q / 3;
       if (2 * i + 1 < CiF && o < Co) {
         const float wa = Fp[((size_t)o * CiF + 2 * i) * Kp + col0 + (k & 15)], wb = Fp[((size_t)o * CiF + 2 * i + 1) * Kp + col0 + (k & 15)];
         w = (ty == 0) ? wa + wb : (ty == 1) ? wa : wb;

@@ -515,6 +515,10 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis, keep_aligned=False):
     b, n, k = idx.shape
     E = b * n * k
     dev = idx.device
+    if isinstance(basis, dict):
+        raise TypeError("ConvSE3 takes the basis as the tuple (flat buffer, BasisPlan, Geometry) that SE3Transformer.forward builds: "
+                        "`ops.basis_flat(rel_pos, max_degree) + (model.Geometry(rel_pos, max_degree),)`; the dict returned by the "
+                        "drop-in get_basis() is the reference's per-pair view of the same buffer and is not accepted here")
     flat, plan = basis[:2]                   # BasisFlat (+ Geometry)
     geom = basis[2] if len(basis) > 2 else None
     bpairs = ops.basis_pairs(flat, plan, E)

@@ -142,6 +142,23 @@ def knn(coors, k, valid_radius, node_mask=None, neighbor_mask=None, sparse_adj=N
     _require_cuda(coors, node_mask, neighbor_mask, sparse_adj)
     coors = _f32(coors)
     b, n, _ = coors.shape
+    # the kernel indexes the masks as [b, n] / [b, n, n]: broadcastable inputs ([n, n], [1, n, n]) are expanded here, anything
+    # else is refused instead of being read out of bounds
+    if node_mask is not None:
+        if node_mask.shape != (b, n):
+            raise ValueError(f'knn: node_mask must be [b, n] = {(b, n)}, got {tuple(node_mask.shape)}')
+    pair = []
+    for name, t in (('neighbor_mask', neighbor_mask), ('sparse_adj', sparse_adj)):
+        if t is not None:
+            if t.dim() == 2:
+                t = t.unsqueeze(0)
+            if t.shape[-2:] != (n, n) or t.shape[0] not in (1, b):
+                raise ValueError(f'knn: {name} must be [n, n], [1, n, n] or [b, n, n] with b, n = {(b, n)}, got {tuple(t.shape)}')
+            t = t.expand(b, n, n)
+        pair.append(t)
+    neighbor_mask, sparse_adj = pair
+    if not 1 <= k <= n - 1:
+        raise ValueError(f'knn: k = {k} must be in [1, n - 1] = [1, {n - 1}]')
     idx = torch.empty((b, n, k), dtype=torch.int64, device=coors.device)
     mask = torch.empty((b, n, k), dtype=torch.uint8, device=coors.device)
     rel_pos = torch.empty((b, n, k, 3), dtype=torch.float32, device=coors.device)
