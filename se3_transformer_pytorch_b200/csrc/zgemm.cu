@@ -32,6 +32,9 @@
 
 namespace se3 {
 
+#ifndef SE3_Z_ISSUERS3
+#define SE3_Z_ISSUERS3 1
+#endif
 constexpr int kZThreads = 384;
 constexpr int kZMaxSeg = 16;
 constexpr uint32_t kZTmemCols = 512;
@@ -98,6 +101,10 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   constexpr int WS = kZWRingBytes / kStageBytes;          // W ring depth (stages)
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
+  // MMA-issuing warps.  One thread issues an N = 128 tcgen05.mma only every ~85 cycles (measured: 72 % tensor-pipe utilisation in
+  // MODE 3 whatever the generators do, 92 % in MODE 1 whose N = 256 instructions last 128 cycles), so MODE 3 uses three issuers,
+  // warps 1-3, one per accumulator / weight set; every hand-off barrier then counts three commits.
+  constexpr int NI = (MODE == 3 && SE3_Z_ISSUERS3) ? 3 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -127,13 +134,13 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < WS; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, CSZ);
+      mbar_init(bar_w_empty + 8 * s, CSZ * NI);
     }
     for (int s = 0; s < AS; ++s) {
       mbar_init(bar_a_full + 8 * s, 4);
-      mbar_init(bar_a_empty + 8 * s, 1);
+      mbar_init(bar_a_empty + 8 * s, NI);
     }
-    mbar_init(bar_d_full, 1);
+    mbar_init(bar_d_full, NI);
     mbar_init(bar_d_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -169,8 +176,9 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
+    } else if (warp == 1 || (NI == 3 && warp <= 3)) {
+      // ===================== MMA issuer(s) =====================
+      const int my_ty = warp - 1;                   // NI == 3: the accumulator (weight set) this warp feeds
       int blk_start = 0, blk = 0;
       for (int s = 0; s < S; ++s) {
         const int wslot = s % WS, aslot = s % AS;
@@ -196,21 +204,36 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
               accum = 1u;
             }
           } else if (MODE == 3) {
-            // chunk c of stage s belongs to weight set (s + c) % 3 (every segment has a multiple of 3 stages); pass-major order:
-            // consecutive MMAs hit S1, S2, S3, S1' in turn
-            const int blk_first = (s == blk_start);
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int ty = (s + c) % 3;
-                const uint32_t d = tmem_base + (uint32_t)(ty * 128);
+            // chunk c of stage s belongs to weight set (s + c) % 3 (every segment has a multiple of 3 stages)
+            if (NI == 3) {
+              // this issuer: the chunks of ITS set, (c - my_ty + s) % 3 == 0 -> c0 = (my_ty - s) mod 3, and c0 + 3 if that is 3
+              const int c0 = ((my_ty - s) % 3 + 3) % 3;
+              uint32_t accum = (s == blk_start) ? 0u : 1u;
+              const uint32_t d = tmem_base + (uint32_t)(my_ty * 128);
+              for (int c = c0; c < 4; c += 3) {
                 const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
                 const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
                 const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
-                // first MMA into an accumulator in this block overwrites it: pass 0 of chunks 0..2 of the block's first stage
-                const uint32_t accum = (blk_first && pass == 0 && c < 3) ? 0u : 1u;
-                tc_mma_f16_ts(d, pass == 1 ? a_hi + 8 : a_hi, pass == 2 ? b_lo : b_hi, kIdesc, accum);
+                tc_mma_f16_ts(d, a_hi, b_hi, kIdesc, accum);
+                tc_mma_f16_ts(d, a_hi + 8, b_hi, kIdesc, 1u);
+                tc_mma_f16_ts(d, a_hi, b_lo, kIdesc, 1u);
+                accum = 1u;
+              }
+            } else {
+              // one issuer, pass-major order: consecutive MMAs hit S1, S2, S3, S1' in turn
+              const int blk_first = (s == blk_start);
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int ty = (s + c) % 3;
+                  const uint32_t d = tmem_base + (uint32_t)(ty * 128);
+                  const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
+                  const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
+                  const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+                  const uint32_t accum = (blk_first && pass == 0 && c < 3) ? 0u : 1u;
+                  tc_mma_f16_ts(d, pass == 1 ? a_hi + 8 : a_hi, pass == 2 ? b_lo : b_hi, kIdesc, accum);
+                }
               }
             }
           } else {
