@@ -157,8 +157,6 @@ def knn(coors, k, valid_radius, node_mask=None, neighbor_mask=None, sparse_adj=N
             t = t.expand(b, n, n)
         pair.append(t)
     neighbor_mask, sparse_adj = pair
-    if not 1 <= k <= n - 1:
-        raise ValueError(f'knn: k = {k} must be in [1, n - 1] = [1, {n - 1}]')
     idx = torch.empty((b, n, k), dtype=torch.int64, device=coors.device)
     mask = torch.empty((b, n, k), dtype=torch.uint8, device=coors.device)
     rel_pos = torch.empty((b, n, k, 3), dtype=torch.float32, device=coors.device)

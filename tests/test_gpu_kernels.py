@@ -413,3 +413,13 @@ def test_errors_are_loud():
         ops.knn(torch.randn(1, 4, 3, device=DEV), 9, 1e5)
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.knn(torch.randn(1, 4, 3), 2, 1e5)
+    # mask shapes: [n, n] / [1, n, n] broadcast over the batch, anything else is refused (not read out of bounds)
+    c = torch.randn(2, 6, 3, device=DEV)
+    nm = torch.rand(6, 6, device=DEV) > 0.3
+    a = ops.knn(c, 3, 1e5, neighbor_mask=nm)
+    b_ = ops.knn(c, 3, 1e5, neighbor_mask=nm.unsqueeze(0).expand(2, 6, 6).contiguous())
+    assert all(torch.equal(x, y) for x, y in zip(a, b_))
+    with pytest.raises(ValueError, match='neighbor_mask'):
+        ops.knn(c, 3, 1e5, neighbor_mask=torch.ones(3, 6, 6, dtype=torch.bool, device=DEV))
+    with pytest.raises(ValueError, match='node_mask'):
+        ops.knn(c, 3, 1e5, node_mask=torch.ones(6, dtype=torch.bool, device=DEV))
