@@ -378,57 +378,22 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         for (int j = 0; j < ACC; ++j) dst[(size_t)j * M] = acc[j] * inv + (res ? __ldg(res + (size_t)j * M) : 0.f);
       }
     } else {
-    // position of this warp's next stage: (segment, local stage)
-    int seg = 0, sl = h;
-    while (seg < prm.n_seg && sl >= prm.seg[seg].n_stage) { sl -= prm.seg[seg].n_stage; ++seg; }
-    int s = h;                                 // global stage index
-    int cur_seg = -1;
+    // ---- generators of MODE 1 / 2 / 3: warp h fills the stages of parity h.  Lean loop: the segment's constants live in
+    // registers, positions are running counters (ncu r02b: 391 instructions per stage of which only 128 were the outer product;
+    // the generation latency of a stage, not the tensor pipe, bounded MODE 3)
     __half2 Uh[8], Ul[8];                      // the segment's radial coordinates U[e, 0..15], split hi / lo
-    const float* Xp = nullptr;                 // component row(s) of this thread inside the current segment's X
-    int xstride = 0, cp = 0, cm = 0, Ci = 0;
-
-    constexpr int NX = (MODE == 3) ? 8 : 4;
-    auto load_x = [&](int sg, int stage_local, float (&xv)[NX]) {
-      const ZSeg& z = prm.seg[sg];
-      const float* xb = z.X + ((size_t)mt * z.Ci * z.ncomp) * 128 + el;
-      if (MODE == 3) {
-        // chunk c of the stage = K chunk q = 4 stage + c of the segment: input channel q / 3, weight set q % 3.  Raw loads only:
-        // combining them here would wait for the loads at once and expose the memory latency of every stage (ncu: 14 % of all
-        // stall samples on that FADD); c, d - c, c + d are formed when the stage is generated
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = (stage_local * 4 + c) / 3;
-          xv[c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
-          xv[4 + c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
-        }
-      } else if (MODE == 1) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = stage_local * 4 + c;
-          xv[c] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int il = 0; il < 2; ++il) {
-          const int i = stage_local * 2 + il;
-          xv[2 * il] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cplus) * 128) : 0.f;
-          xv[2 * il + 1] = (i < z.Ci) ? __ldg(xb + ((size_t)i * z.ncomp + z.cminus) * 128) : 0.f;
-        }
-      }
-    };
-    (void)Xp; (void)xstride; (void)cp; (void)cm; (void)Ci;
-
-    float xv[NX], xn[NX];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) { xv[c] = 0.f; xn[c] = 0.f; }
-    if (seg < prm.n_seg) load_x(seg, sl, xv);
-    while (seg < prm.n_seg) {
-      // next stage of this warp (two global stages ahead): prefetch its neighbour features
-      int nseg = seg, nsl = sl + 2;
-      while (nseg < prm.n_seg && nsl >= prm.seg[nseg].n_stage) { nsl -= prm.seg[nseg].n_stage; ++nseg; }
-      if (nseg < prm.n_seg) load_x(nseg, nsl, xn);
-      if (seg != cur_seg) {
-        const float4* urow = reinterpret_cast<const float4*>(prm.seg[seg].U + (size_t)(live ? eg : 0) * 64);
+    constexpr int NX = (MODE == 1) ? 4 : 8;
+    constexpr int LOG_AS = (AS == 4) ? 2 : 1;
+    static_assert(AS == (1 << LOG_AS), "A ring depth");
+    int s0 = 0;                                // global index of the current segment's first stage
+    int next_drain = min(FS, S) - 1 + AS;      // block `flushed` is drained before generating a stage s >= next_drain
+    for (int sg = 0; sg < prm.n_seg; ++sg) {
+      const int ns = prm.seg[sg].n_stage, ncomp = prm.seg[sg].ncomp;
+      const size_t istride = (size_t)ncomp * 128;                       // floats between consecutive input channels of X
+      const float* xp = prm.seg[sg].X + ((size_t)mt * prm.seg[sg].Ci * ncomp + prm.seg[sg].cplus) * 128 + el;
+      const float* xm = prm.seg[sg].X + ((size_t)mt * prm.seg[sg].Ci * ncomp + prm.seg[sg].cminus) * 128 + el;
+      {
+        const float4* urow = reinterpret_cast<const float4*>(prm.seg[sg].U + (size_t)(live ? eg : 0) * 64);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const float4 u4 = live ? __ldg(urow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,48 +403,81 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
           Ul[2 * v] = __floats2half2_rn(u4.x - f0.x, u4.y - f0.y);
           Ul[2 * v + 1] = __floats2half2_rn(u4.z - f1.x, u4.w - f1.y);
         }
-        cur_seg = seg;
       }
-      // drain every accumulation block that ended at least AS stages ago (the MMA warp cannot run further ahead anyway)
-      while (flushed < n_blk && min((flushed + 1) * FS, S) - 1 <= s - AS) drain();
-      const int aslot = s % AS;
-      mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(s / AS) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT);
-      if (MODE == 1 || MODE == 3) {
+      // raw loads only (MODE 3: combining x+ / x- at load time would wait for the loads at once and expose the memory latency of
+      // every stage; c, d - c, c + d are formed when the stage is generated).  (C_in F) % 4 == 0: every chunk of a stage is valid.
+      auto load_x = [&](int sl, float (&x)[NX]) {
+        if (MODE == 1) {
+          const float* p0 = xp + (size_t)(4 * sl) * istride;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[16];
-          float y = xv[c];
-          if (MODE == 3) {
-            const int ty = (sl + c) % 3;                         // weight set (a+b, a, b) <-> y = (c, d - c, c + d)
-            y = (ty == 0) ? xv[c] : (ty == 1) ? (xv[4 + c] - xv[c]) : (xv[c] + xv[4 + c]);
+          for (int c = 0; c < 4; ++c) x[c] = __ldg(p0 + c * istride);
+        } else if (MODE == 2) {
+          const size_t o = (size_t)(2 * sl) * istride;
+#pragma unroll
+          for (int il = 0; il < 2; ++il) { x[2 * il] = __ldg(xp + o + il * istride); x[2 * il + 1] = __ldg(xm + o + il * istride); }
+        } else {
+          // chunk c of the stage = K chunk q = 4 sl + c of the segment: input channel q / 3, weight set q % 3
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const size_t o = (size_t)((4 * sl + c) / 3) * istride;
+            x[c] = __ldg(xp + o);
+            x[4 + c] = __ldg(xm + o);
           }
-          z_outer16(Uh, Ul, y * sxe, r);
-          tmem_st16(a0 + (uint32_t)(c * 16), r);
         }
-      } else {
+      };
+      int sl = (s0 ^ h) & 1;                   // this warp's first stage of the segment
+      float xv[NX];
 #pragma unroll
-        for (int il = 0; il < 2; ++il) {
-          uint32_t rP[16], rM[16], nM[16];
-          z_outer16(Uh, Ul, xv[2 * il] * sxe, rP);
-          z_outer16(Uh, Ul, xv[2 * il + 1] * sxe, rM);
+      for (int c = 0; c < NX; ++c) xv[c] = 0.f;
+      if (sl < ns) load_x(sl, xv);
+#pragma unroll 1
+      for (; sl < ns; sl += 2) {
+        const int s = s0 + sl;
+        float xn[NX];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) nM[j] = rM[j] ^ 0x80008000u;
-          // component +m: (f = a: U x+), (f = b: -U x-);   component -m: (f = a: U x-), (f = b: U x+)
-          tmem_st16(a0 + (uint32_t)((2 * il) * 16), rP);
-          tmem_st16(a0 + (uint32_t)((2 * il + 1) * 16), nM);
-          tmem_st16(a0 + (uint32_t)(64 + (2 * il) * 16), rM);
-          tmem_st16(a0 + (uint32_t)(64 + (2 * il + 1) * 16), rP);
+        for (int c = 0; c < NX; ++c) xn[c] = 0.f;
+        if (sl + 2 < ns) load_x(sl + 2, xn);   // this warp's next stage: prefetched one generation ahead
+        // drain every accumulation block that ended at least AS stages ago (the MMA warp cannot run further ahead anyway)
+        while (flushed < n_blk && s >= next_drain) { drain(); next_drain = min((flushed + 1) * FS, S) - 1 + AS; }
+        const int aslot = s & (AS - 1);
+        mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(s >> LOG_AS) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t a0 = tmem_base + t_lane + kZACol + (uint32_t)(aslot * ASLOT);
+        if (MODE == 1 || MODE == 3) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[16];
+            float y = xv[c];
+            if (MODE == 3) {
+              const int ty = (sl + c) % 3;                         // weight set (a+b, a, b) <-> y = (c, d - c, c + d)
+              y = (ty == 0) ? xv[c] : (ty == 1) ? (xv[4 + c] - xv[c]) : (xv[c] + xv[4 + c]);
+            }
+            z_outer16(Uh, Ul, y * sxe, r);
+            tmem_st16(a0 + (uint32_t)(c * 16), r);
+          }
+        } else {
+#pragma unroll
+          for (int il = 0; il < 2; ++il) {
+            uint32_t rP[16], rM[16], nM[16];
+            z_outer16(Uh, Ul, xv[2 * il] * sxe, rP);
+            z_outer16(Uh, Ul, xv[2 * il + 1] * sxe, rM);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) nM[j] = rM[j] ^ 0x80008000u;
+            // component +m: (f = a: U x+), (f = b: -U x-);   component -m: (f = a: U x-), (f = b: U x+)
+            tmem_st16(a0 + (uint32_t)((2 * il) * 16), rP);
+            tmem_st16(a0 + (uint32_t)((2 * il + 1) * 16), nM);
+            tmem_st16(a0 + (uint32_t)(64 + (2 * il) * 16), rM);
+            tmem_st16(a0 + (uint32_t)(64 + (2 * il + 1) * 16), rP);
+          }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
+#pragma unroll
+        for (int c = 0; c < NX; ++c) xv[c] = xn[c];
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
-#pragma unroll
-      for (int c = 0; c < NX; ++c) xv[c] = xn[c];
-      seg = nseg; sl = nsl; s += 2;
+      s0 += ns;
     }
     while (flushed < n_blk) drain();
 
