@@ -36,6 +36,9 @@ WORKLOADS = {
     # reduced-width variants for quick iteration (NOT the headline)
     'cfg2_d128': dict(ctor=dict(dim=128, heads=8, dim_head=16, depth=6, num_degrees=4, num_neighbors=16), b=4, n=1024),
     'cfg2_depth1': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=1, num_degrees=4, num_neighbors=16), b=4, n=1024),
+    # weights-sensitivity experiment: Fourier-encoded distances make the radial functions rougher (higher rank of the radial model)
+    'cfg2_depth1_fourier': dict(ctor=dict(dim=512, heads=8, dim_head=64, depth=1, num_degrees=4, num_neighbors=16, fourier_encode_dist=True,
+                                          rel_dist_num_fourier_features=4), b=4, n=1024),
 }
 
 
