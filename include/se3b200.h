@@ -152,6 +152,13 @@ int se3_pairwise_lr_trace(const float* U, const void* w_img, const float* T, int
 int se3_radial_trunk_u_fwd(const float* feat, int64_t E, int in_dim, int num_pairs, const float* params, const float* V,
                            const float* gmean, const int* ones_col, float* out_g, float* out_U, float* stats, void* stream);
 
+/* Radial coordinates by table lookup (distance-only radial functions): out_U as se3_radial_trunk_u_fwd, interpolated (4-point
+ * Lagrange) from table [num_pairs, G, KT] fp32 = U(d) sampled on the uniform grid d_i = i Dmax / (G - 1) (built in float64 with
+ * the plan; columns >= r zero), dist [E] the neighbour distances.  A distance outside [0, Dmax] (or NaN) sets stats[pair] = (1, 1):
+ * the plan does not cover this forward. */
+int se3_radial_table_fwd(const float* dist, int64_t E, const float* table, int G, int KT, float Dmax, const int* ones_col,
+                         int num_pairs, float* out_U, float* stats, void* stream);
+
 /* Per-edge frames: R_e takes the polar axis a = (0,1,0) of the reference's harmonics (basis.py:57-95) to the direction of
  * rel_pos[e]; D_out[l] [E, 2l+1, 2l+1] = real Wigner matrix D_l(R_e) in the reference's basis, l = 1..lmax <= 5, computed in
  * float64 as Y_l(R x_s) pinv(Y_l(x_s)) from the tables xs[l] [n_samples[l], 3] / pin[l] [2l+1, n_samples[l]] (device, float64).

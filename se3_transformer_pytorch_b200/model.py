@@ -300,12 +300,16 @@ class ConvSE3(nn.Module):
             feat = self.encode_dist(grid)
             pairs = {}
             bases = {}
+            ugrid = {}
             for di, do in self.pairs:
                 pc = self.kernel_unary[f'({di},{do})']
                 if self.tc_eligible(di, do) and pc.rp.net['6'].weight.numel() > 0:
-                    basis = ops.lowrank_basis(pc.rp.trunk64(feat))
+                    G64 = pc.rp.trunk64(feat)
+                    basis = ops.lowrank_basis(G64)
                     if basis is not None:
                         bases[(di, do)] = basis
+                        ugrid[(di, do)] = ((G64 - basis[2]) @ basis[1], float(G64.abs().max()))     # U(d) on the grid, float64
+                    del G64
             # the edge-aligned images serve a ConvSE3 only if EVERY pair has a plan (all launches of an output degree then
             # accumulate in the aligned frame); otherwise keep the global-frame images of 4.2-4.3 for the covered pairs
             aligned_images = use_aligned() and len(bases) == len(self.pairs)
@@ -365,9 +369,39 @@ class ConvSE3(nn.Module):
                         img, S = ops.zgemm_image([(fps.pop((di, do, m)), mi) for di, mi in degs], mo, mode)
                         zplan[(do, m)] = dict(img=img, S=S, degs=degs, mode=mode)
                 del fps
-        plan = dict(D=D, pairs=pairs, z=zplan)
+            utab = self.radial_table(ugrid, bases, grid, dev) if len(bases) == len(self.pairs) and use_utable() else None
+            del ugrid
+        plan = dict(D=D, pairs=pairs, z=zplan, utab=utab)
         pk['lr'] = plan
         return plan
+
+    UTABLE_TOL = 2e-7        # max interpolation error of the tabulated radial coordinates relative to max|g| (float64, grid midpoints)
+
+    def radial_table(self, ugrid, bases, grid, dev):
+        """The radial coordinates U(d) = (g(d) - gmean) V of every pair tabulated on the plan's uniform distance grid (float64 ->
+        fp32 [pairs, G, KT]); the forward interpolates them (se3_radial_table_fwd, 4-point Lagrange) instead of evaluating the MLP
+        per edge.  Accepted only if the interpolant reproduces the float64 trunk at the grid MIDPOINTS to UTABLE_TOL (smooth
+        radial functions pass by orders of magnitude; a rougher one falls back to se3_radial_trunk_u_fwd)."""
+        Gn = grid.shape[0]
+        KT = max(16 * ((bases[p][0] + 1 + 15) // 16) for p in self.pairs)
+        tab = torch.zeros((len(self.pairs), Gn, KT), dtype=torch.float32, device=dev)
+        mid = (grid[:-1] + grid[1:]) * 0.5
+        featm = self.encode_dist(mid)
+        worst = 0.0
+        for pi, pair in enumerate(self.pairs):
+            r, V, gmean = bases[pair]
+            Ug, gmax = ugrid[pair]
+            tab[pi, :, :r] = Ug.float()
+            pc = self.kernel_unary[f'({pair[0]},{pair[1]})']
+            exact = (pc.rp.trunk64(featm) - gmean) @ V                                      # [G-1, r] float64
+            T = tab[pi, :, :r].double()
+            i0 = torch.arange(Gn - 1, device=dev).clamp(1, Gn - 3)                          # as the kernel chooses its 4 nodes
+            f = (torch.arange(Gn - 1, device=dev, dtype=torch.float64) + 0.5 - i0).unsqueeze(-1)
+            w = (-f * (f - 1) * (f - 2) / 6, (f + 1) * (f - 1) * (f - 2) / 2, -(f + 1) * f * (f - 2) / 2, (f + 1) * f * (f - 1) / 6)
+            interp = sum(w[j] * T[i0 - 1 + j] for j in range(4))
+            worst = max(worst, float((interp - exact).abs().max()) / max(gmax, 1e-30))
+        self.utable_error = worst
+        return tab if worst <= self.UTABLE_TOL else None
 
     def zgemm_eligible(self, kps):
         """Shapes the one-GEMM kernel takes: every C_out a multiple of 128, every C_in a multiple of 4 (one stage = 64 K values),
@@ -429,6 +463,11 @@ def input_side(di, do):
 def use_zgemm():
     """One GEMM per (degree_out, |m|) with the A operand generated on the fly instead of the R-first kernels."""
     return not os.environ.get('SE3B200_NO_ZGEMM')
+
+
+def use_utable():
+    """Radial coordinates by table lookup (se3_radial_table_fwd) instead of the per-edge radial MLP (se3_radial_trunk_u_fwd)."""
+    return not os.environ.get('SE3B200_NO_UTABLE')
 
 
 def z_mode_m():
@@ -562,7 +601,11 @@ def conv_forward(convs, inp, edge_info, rel_dist, basis, keep_aligned=False):
             # trunk + U = G V + the residual statistics of the cached subspace on THIS forward's edges, one kernel
             covered = len(lr_plan['pairs']) == len(conv.pairs)
             stats = torch.zeros((len(conv.pairs), 2), dtype=torch.float32, device=dev)
-            U, g = ops.radial_trunk_u(feat, pk['trunk'], lr_plan['Vstack'], lr_plan['gmean'], lr_plan['ones_col'], stats, want_g=not covered)
+            if covered and lr_plan.get('utab') is not None and use_utable():
+                # distance-only radial functions: U(d) interpolated from the plan's float64 table; the guard is the table's range
+                U, g = ops.radial_table(rel_dist, lr_plan['utab'], lr_plan['D'], lr_plan['ones_col'], stats), None
+            else:
+                U, g = ops.radial_trunk_u(feat, pk['trunk'], lr_plan['Vstack'], lr_plan['gmean'], lr_plan['ones_col'], stats, want_g=not covered)
             for pi, pair in enumerate(conv.pairs):
                 pp = lr_plan['pairs'].get(pair)
                 if pp is not None:

@@ -41,6 +41,7 @@ _SIGNATURES = {
     'se3_fold_basis_cm_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'se3_rotate_back_fwd': (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_void_p, c_void_p]),
     'se3_radial_trunk_u_fwd': (c_int, [c_void_p, c_int64, c_int, c_int] + [c_void_p] * 8),
+    'se3_radial_table_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'se3_frames_fwd': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 5),
     'se3_rotgather_fwd': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_int64, c_int64, c_void_p, c_void_p]),
     'se3_rotate_pool_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -489,6 +490,20 @@ def radial_trunk_u(feat, params, V, gmean, ones_col, stats, want_g=False):
     with torch.cuda.device(feat.device), _timed('radial_trunk', flops=flops, nbytes=4 * (feat.numel() + params.numel() + V.numel() + U.numel())):
         _check(lib().se3_radial_trunk_u_fwd(_p(feat), E, in_dim, num_pairs, _p(params), _p(V), _p(gmean), _p(ones_col), _p(g), _p(U), _p(stats), _stream()))
     return U, g
+
+
+def radial_table(dist, table, Dmax, ones_col, stats):
+    """Radial coordinates by table lookup: dist [E] fp32, table [pairs, G, KT] fp32 (U(d) on the uniform grid of [0, Dmax]),
+    ones_col [pairs] int32, stats [pairs, 2] (out-of-range flag) -> U [pairs, E, 64]."""
+    _require_cuda(dist, table, ones_col, stats)
+    dist = _f32(dist).reshape(-1)
+    E = dist.numel()
+    num_pairs, G, KT = table.shape
+    assert table.is_contiguous() and table.dtype == torch.float32 and ones_col.dtype == torch.int32
+    U = torch.empty((num_pairs, E, 64), dtype=torch.float32, device=dist.device)
+    with torch.cuda.device(dist.device), _timed('radial_table', flops=8 * E * num_pairs * KT, nbytes=4 * (E + U.numel() + 4 * E * num_pairs * KT)):
+        _check(lib().se3_radial_table_fwd(_p(dist), E, _p(table), G, KT, float(Dmax), _p(ones_col), num_pairs, _p(U), _p(stats), _stream()))
+    return U
 
 
 _FRAME_TABLES = {}

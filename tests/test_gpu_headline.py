@@ -153,8 +153,11 @@ def test_production_path_matches_simt_whole_model():
         assert err < TOL, f'degree {d}: {err:.3e}'
 
 
-def test_plan_guard_bounds_the_output_error():
-    """The run-time guard of the low-rank plan is on the radial trunk outputs (max |g - gmean - U V^T| <= 1e-5 max |g| on the edges
+@pytest.mark.parametrize('radial', ['mlp', 'table'])
+def test_plan_guard_bounds_the_output_error(radial, monkeypatch):
+    """(radial = 'mlp': per-edge radial MLP + residual guard, SE3B200_NO_UTABLE=1; 'table': the default, radial coordinates
+    interpolated from the plan's table, whose guard is the tabulated distance range.)
+    The run-time guard of the low-rank plan is on the radial trunk outputs (max |g - gmean - U V^T| <= 1e-5 max |g| on the edges
     of the forward), the contract on the outputs (1e-4).  Drive a model with released masters (plan built for distances <= 2) with
     growing point clouds until the guard rejects the input: every ACCEPTED forward -- including the ones whose residual sits just
     below the guard -- must match the direct K = 128 kernels of an identical model within 1e-4, and the first rejected one must
@@ -163,6 +166,8 @@ def test_plan_guard_bounds_the_output_error():
     from se3_transformer_pytorch_b200 import SE3Transformer, ops, model as M
     if not ops.tc_supported(DEV, 128, 1):
         pytest.skip('needs sm_100')
+    if radial == 'mlp':
+        monkeypatch.setenv('SE3B200_NO_UTABLE', '1')
     ctor = dict(dim=128, heads=2, dim_head=64, depth=1, num_degrees=3, output_degrees=2, num_neighbors=8)
     torch.manual_seed(5)
     with torch.device(DEV):
@@ -200,7 +205,7 @@ def test_plan_guard_bounds_the_output_error():
         assert M.LAST_PLAN_RESIDUAL <= M.ConvSE3.LR_RUNTIME_TOL
         assert err < TOL, f'scale {scale}: residual {M.LAST_PLAN_RESIDUAL:.2e} was accepted but the output is off by {err:.2e}'
     os.makedirs('gpurun_out', exist_ok=True)
-    with open('gpurun_out/plan_guard.jsonl', 'w') as f:
+    with open(f'gpurun_out/plan_guard_{radial}.jsonl', 'w') as f:
         for r in rows:
             f.write(json.dumps(r) + '\n')
     print(rows)

@@ -302,3 +302,28 @@ def test_linear_tc_matches_fp64(D, Eo, M, nodes, with_res):
     # 3-pass fp16 split (~2^-21 per product) + fp32 partial sums: a few 1e-6 of the row's scale
     assert float(((out.double() - ref).abs() / scale).max()) < 6e-6
     assert float(out[0, 3].abs().max()) == 0.0 or with_res
+
+
+def test_radial_table_matches_trunk_kernel():
+    """Radial coordinates by table lookup (se3_radial_table_fwd, 4-point Lagrange on the plan's float64 grid) vs the per-edge
+    radial MLP + projection (se3_radial_trunk_u_fwd) on the same distances; out-of-range distances raise the flag."""
+    from se3_transformer_pytorch_b200 import ops
+    from se3_transformer_pytorch_b200.model import ConvSE3, Fiber
+    torch.manual_seed(0)
+    conv = ConvSE3(Fiber.create(2, 128), Fiber.create(2, 128), pool=False, self_interaction=False).to(DEV)
+    plan = conv.lowrank_plan(4.0)
+    assert plan['utab'] is not None and conv.utable_error < 2e-7, conv.utable_error
+    pairs = len(conv.pairs)
+    Vs = torch.stack([plan['pairs'][p]['V'] for p in conv.pairs]).contiguous()
+    gm = torch.stack([plan['pairs'][p]['gmean'] for p in conv.pairs]).contiguous()
+    ones = torch.tensor([plan['pairs'][p]['r'] for p in conv.pairs], dtype=torch.int32, device=DEV)
+    d = torch.cat([torch.rand(5000, device=DEV) * 4.0, torch.tensor([0.0, 4.0, plan['D']], device=DEV)])
+    stats_t, stats_k = torch.zeros(pairs, 2, device=DEV), torch.zeros(pairs, 2, device=DEV)
+    Ut = ops.radial_table(d, plan['utab'], plan['D'], ones, stats_t)
+    Uk, _ = ops.radial_trunk_u(d.unsqueeze(-1).contiguous(), conv.packed()['trunk'], Vs, gm, ones, stats_k)
+    assert float((Ut - Uk).abs().max()) < 3e-6 * max(1.0, float(Uk.abs().max()))     # the fp32 MLP itself is ~1e-6 off float64
+    assert float(stats_t.abs().max()) == 0.0
+    ops.radial_table(torch.tensor([1.0, plan['D'] * 1.01], device=DEV), plan['utab'], plan['D'], ones, stats_t)
+    assert bool((stats_t == 1).all())
+    ops.radial_table(torch.tensor([float('nan')], device=DEV), plan['utab'], plan['D'], ones, stats_k.zero_())
+    assert bool((stats_k == 1).all())

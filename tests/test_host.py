@@ -183,6 +183,20 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
         U[torch.arange(len(conv.pairs)), :, ones_col.long()] = 1.0
         return U.float(), (g.float() if want_g else None)
 
+    def radial_table(dist, table, Dmax, ones_col, stats):
+        # float64 restatement of se3_radial_table_fwd: 4-point Lagrange interpolation of the plan's U(d) table
+        d = dist.reshape(-1).double()
+        assert float(d.max()) <= Dmax
+        Gn, KT = table.shape[1], table.shape[2]
+        t = d * (Gn - 1) / Dmax
+        i0 = t.floor().long().clamp(1, Gn - 3)
+        f = (t - i0).unsqueeze(-1)
+        w = (-f * (f - 1) * (f - 2) / 6, (f + 1) * (f - 1) * (f - 2) / 2, -(f + 1) * f * (f - 2) / 2, (f + 1) * f * (f - 1) / 6)
+        U = torch.zeros(table.shape[0], d.numel(), 64, dtype=torch.float64)
+        U[:, :, :KT] = sum(w[j] * table.double()[:, i0 - 1 + j] for j in range(4))
+        U[torch.arange(table.shape[0]), :, ones_col.long()] = 1.0
+        return U.float()
+
     def rotgather(x, idx, D, tile_begin=0, tile_count=None, out=None):
         E = idx.numel()
         e0, e1 = tile_begin * ops.TILE_E, min(E, (tile_begin + tile_count) * ops.TILE_E)
@@ -268,7 +282,7 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
 
     for name, fn in (('radial_trunk', radial_trunk), ('tbuild_blocks', tbuild_blocks), ('pairwise_lr', pairwise_lr),
                      ('rotate_back', rotate_back), ('tbuild', tbuild), ('gather_tiles', gather_tiles), ('fold_basis', fold_basis),
-                     ('radial_trunk_u', radial_trunk_u), ('rotgather', rotgather), ('edge_scale', edge_scale), ('zgemm_image', zgemm_image),
+                     ('radial_trunk_u', radial_trunk_u), ('radial_table', radial_table), ('rotgather', rotgather), ('edge_scale', edge_scale), ('zgemm_image', zgemm_image),
                      ('zgemm', zgemm)):
         monkeypatch.setattr(ops, name, fn)
 
