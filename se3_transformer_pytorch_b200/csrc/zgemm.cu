@@ -32,6 +32,11 @@
 
 namespace se3 {
 
+// timing experiments only (results are wrong): move only 1 / SE3_Z_DBG_WDIV of every weight stage (how much of the power budget
+// does the L2 -> shared-memory weight stream take?)
+#ifndef SE3_Z_DBG_WDIV
+#define SE3_Z_DBG_WDIV 1
+#endif
 #ifndef SE3_Z_ISSUERS3
 #define SE3_Z_ISSUERS3 1
 #endif
@@ -160,15 +165,16 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
     if (warp == 0) {
       // ===================== weight producer =====================
       const uint8_t* wsrc = prm.w_img + (size_t)nt * S * kStageBytes;
-      constexpr uint32_t kShare = kStageBytes / CSZ;
+      constexpr uint32_t kMove = kStageBytes / SE3_Z_DBG_WDIV;
+      constexpr uint32_t kShare = kMove / CSZ;
       for (int s = 0; s < S; ++s) {
         const int slot = s % WS;
         const uint32_t ph = (uint32_t)(s / WS) & 1u;
         mbar_wait(bar_w_empty + 8 * slot, ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kStageBytes);
+          mbar_arrive_expect_tx(bar_w_full + 8 * slot, kMove);
           if (CSZ == 1) {
-            bulk_g2s(sW + slot * kStageBytes, wsrc + (size_t)s * kStageBytes, kStageBytes, bar_w_full + 8 * slot);
+            bulk_g2s(sW + slot * kStageBytes, wsrc + (size_t)s * kStageBytes, kMove, bar_w_full + 8 * slot);
           } else {
             bulk_g2s_mc(sW + slot * kStageBytes + crank * kShare, wsrc + (size_t)s * kStageBytes + crank * kShare, kShare,
                         bar_w_full + 8 * slot, kMask);
@@ -679,7 +685,8 @@ extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img,
   prm.S = S;
   // default drain period: 96 accumulating tcgen05.mma per accumulator (8 stages of 12; mode 3 spreads its stages over three
   // accumulators): rel. error 4e-6 against float64 for all-positive operands at K = 65536 (2.5e-4 if never drained)
-  prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages : z_env_int("SE3B200_Z_FLUSH", mode == 3 ? 24 : 8));
+  prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages
+                                                     : z_env_int("SE3B200_Z_FLUSH", mode == 3 ? 24 : 8) * std::max(1, z_env_int("SE3B200_Z_FLUSH_MULT", 1)));
   const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
   cudaStream_t s = as_stream(stream);
   if (mode == 3) return csz == 1 ? launch_z<3, 128, 1>(prm, s) : launch_z<3, 128, 2>(prm, s);

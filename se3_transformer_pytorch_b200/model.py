@@ -375,7 +375,7 @@ class ConvSE3(nn.Module):
         pk['lr'] = plan
         return plan
 
-    UTABLE_TOL = 2e-7        # max interpolation error of the tabulated radial coordinates relative to max|g| (float64, grid midpoints)
+    UTABLE_TOL = 5e-7        # max interpolation error of the tabulated radial coordinates relative to max|g| (float64, grid midpoints)
 
     def radial_table(self, ugrid, bases, grid, dev):
         """The radial coordinates U(d) = (g(d) - gmean) V of every pair tabulated on the plan's uniform distance grid (float64 ->
