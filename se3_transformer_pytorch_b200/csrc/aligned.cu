@@ -121,10 +121,31 @@ rotgather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, c
   const int i0 = blockIdx.y * ci_per_cta, i1 = min(Ci, i0 + ci_per_cta);
   float* Xt = X + ((size_t)mt * Ci * Q) * SE3_TILE_E + el;
   if (Q > 1) __syncthreads();
+  if constexpr (Q > 1 && Q <= 7) {
+    // the edge's Wigner block lives in registers for the whole channel loop (it was Q*Q shared-memory loads per channel)
+    float d[Q * Q];
+#pragma unroll
+    for (int r = 0; r < Q * Q; ++r) d[r] = Ds[r * SE3_TILE_E + el];
+#pragma unroll 2
+    for (int i = i0 + lc; i < i1; i += kRgLanes) {
+      float xv[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xv[q] = valid ? __ldg(xrow + (size_t)i * Q + q) : 0.f;
+#pragma unroll
+      for (int nn = 0; nn < Q; ++nn) {
+        float o = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) o = fmaf(d[q * Q + nn], xv[q], o);
+        Xt[((size_t)i * Q + nn) * SE3_TILE_E] = o;
+      }
+    }
+    return;
+  }
+#pragma unroll 4
   for (int i = i0 + lc; i < i1; i += kRgLanes) {
     float xv[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) xv[q] = valid ? xrow[(size_t)i * Q + q] : 0.f;
+    for (int q = 0; q < Q; ++q) xv[q] = valid ? __ldg(xrow + (size_t)i * Q + q) : 0.f;
 #pragma unroll
     for (int nn = 0; nn < Q; ++nn) {
       float o;
