@@ -16,7 +16,9 @@
 // One CTA = 128 edges x 32 channels, loops over ceil(C_in*f/4) steps; per step one N=128 accumulator tile (column =
 // if_local*32 + o_local), 3 passes (fp16 hi/lo split) x Kp/16 tcgen05.mma with A (= U tile, hi/lo) resident in tensor
 // memory and B tiles (F' image, [hi | lo] x 128 rows x 64 K, SW128) streamed by TMA bulk copies, multicast over a
-// 2-CTA cluster.  640 threads: warp 0 W producer, warp 1 TMEM owner + MMA issuer, warp 2 T producer, warps 4-19 epilogue.
+// 2-CTA cluster.  640 threads: warp 0 W producer, warps 1 and 3 MMA issuers (even / odd steps; warp 1 owns the TMEM allocation),
+// warp 2 T producer, warps 4-19 epilogue.  (Round 2: the production path moved to csrc/zgemm.cu; this kernel
+// serves fibers that are not multiples of 128 channels.)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
