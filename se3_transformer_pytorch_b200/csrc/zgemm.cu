@@ -93,18 +93,31 @@ __device__ __forceinline__ void z_outer16(const __half2 (&Uh)[8], const __half2 
   }
 }
 
-template <int MODE, int N, int CSZ>
+template <bool PAIR>
+__device__ __forceinline__ void z_mma(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR) tc_mma_f16_ts_pair(d, a, bdesc, idesc, accumulate);
+  else z_mma<PAIR>(d, a, bdesc, idesc, accumulate);
+}
+
+template <int MODE, int N, int CSZ, bool PAIR = false>
 __global__ void __launch_bounds__(kZThreads, 1)
 zgemm_kernel(const __grid_constant__ ZParams prm) {
+  // PAIR: the two CTAs of the cluster (neighbouring edge tiles of one channel tile) run as ONE tensor-core pair (cta_group::2):
+  // the leader's MMA covers M = 256 = both edge tiles, each CTA streams only ITS half of every weight stage (rows r N/2 ..) into
+  // its own shared memory -- half the L2 -> shared-memory weight traffic per SM, which costs 15 % of the kernel's time through
+  // the power cap.  Generators, accumulators and drains stay per CTA.
+  static_assert(!PAIR || (CSZ == 2 && (MODE == 1 || MODE == 3)), "pair mode: 2-CTA cluster, MODE 1 / 3");
   static_assert(MODE == 1 || ((MODE == 2 || MODE == 3 || MODE == 4) && N == 128), "MODE 2 / 3 use two / three N = 128 accumulators");
   constexpr int DCOLS = (MODE == 3) ? 384 : (MODE == 2) ? 256 : N;   // accumulator columns in use
   constexpr int ACC = (MODE == 3) ? 128 : DCOLS / 2;      // fp32 partial sums per drain thread (MODE 3: 64 of out'[+], 64 of out'[-])
   constexpr int ASLOT = (MODE == 2) ? 128 : 64;           // TMEM columns of one A stage
   constexpr uint32_t kZACol = (MODE == 3) ? 384 : 256;    // D: columns [0, kZACol); A ring: columns [kZACol, 512)
   constexpr int AS = (512 - (int)kZACol) / ASLOT;         // A ring depth (stages)
-  constexpr uint32_t kStageBytes = 2u * N * 128u;
-  constexpr int WS = kZWRingBytes / kStageBytes;          // W ring depth (stages)
-  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t kImgStage = 2u * N * 128u;            // one stage of the weight image: [hi N rows | lo N rows] x 128 B
+  constexpr uint32_t kStageBytes = PAIR ? kImgStage / 2 : kImgStage;      // what one CTA keeps of it in shared memory
+  constexpr uint32_t kLoOff = PAIR ? (N / 2) * 128u : N * 128u;           // lo part inside a shared-memory stage
+  constexpr int WS = (kZWRingBytes / kStageBytes > 8) ? 8 : (int)(kZWRingBytes / kStageBytes);     // W ring depth (stages)
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
   constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
   // MMA-issuing warps.  One thread issues an N = 128 tcgen05.mma only every ~85 cycles (measured: 72 % tensor-pipe utilisation in
   // MODE 3 whatever the generators do, 92 % in MODE 1 whose N = 256 instructions last 128 cycles), so MODE 3 uses three issuers,
@@ -123,7 +136,8 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   const uint32_t bar_a_empty = bar_a_full + 8 * AS;
   const uint32_t bar_d_full = bar_a_empty + 8 * AS;
   const uint32_t bar_d_empty = bar_d_full + 8;
-  const uint32_t s_tmem_slot = bar_d_empty + 8;
+  const uint32_t bar_peer_full = bar_d_empty + 8;         // [AS] (pair mode, leader): the peer's weights + Z of a stage are in place
+  const uint32_t s_tmem_slot = bar_peer_full + 8 * AS;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -139,20 +153,26 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < WS; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, CSZ * NI);
+      mbar_init(bar_w_empty + 8 * s, PAIR ? NI : CSZ * NI);
     }
     for (int s = 0; s < AS; ++s) {
       mbar_init(bar_a_full + 8 * s, 4);
       mbar_init(bar_a_empty + 8 * s, NI);
     }
     mbar_init(bar_d_full, NI);
-    mbar_init(bar_d_empty, 8);
+    mbar_init(bar_d_empty, PAIR ? 16 : 8);                 // pair mode: the drain warps of both CTAs report to the leader
+    for (int s = 0; s < AS; ++s) mbar_init(bar_peer_full + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kZTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kZTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(kZTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -164,7 +184,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
       // ===================== weight producer =====================
-      const uint8_t* wsrc = prm.w_img + (size_t)nt * S * kStageBytes;
+      const uint8_t* wsrc = prm.w_img + (size_t)nt * S * kImgStage;
       constexpr uint32_t kMove = kStageBytes / SE3_Z_DBG_WDIV;
       constexpr uint32_t kShare = kMove / CSZ;
       for (int s = 0; s < S; ++s) {
@@ -173,7 +193,13 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         mbar_wait(bar_w_empty + 8 * slot, ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_w_full + 8 * slot, kMove);
-          if (CSZ == 1) {
+          if (PAIR) {
+            // this CTA's rows [crank N/2, +N/2) of the hi and of the lo part
+            constexpr uint32_t kHalf = (N / 2) * 128u / SE3_Z_DBG_WDIV;
+            const uint8_t* src = wsrc + (size_t)s * kImgStage + crank * (N / 2) * 128u;
+            bulk_g2s(sW + slot * kStageBytes, src, kHalf, bar_w_full + 8 * slot);
+            bulk_g2s(sW + slot * kStageBytes + kLoOff, src + N * 128u, kHalf, bar_w_full + 8 * slot);
+          } else if (CSZ == 1) {
             bulk_g2s(sW + slot * kStageBytes, wsrc + (size_t)s * kStageBytes, kMove, bar_w_full + 8 * slot);
           } else {
             bulk_g2s_mc(sW + slot * kStageBytes + crank * kShare, wsrc + (size_t)s * kStageBytes + crank * kShare, kShare,
@@ -181,6 +207,18 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
           }
         }
         __syncwarp();
+      }
+    } else if (PAIR && crank != 0) {
+      // ===================== pair mode, peer CTA: relay "my weights and my Z of stage s are in place" to the leader =====================
+      if (warp == 1) {
+        for (int s = 0; s < S; ++s) {
+          mbar_wait(bar_w_full + 8 * (s % WS), (uint32_t)(s / WS) & 1u);
+          mbar_wait(bar_a_full + 8 * (s % AS), (uint32_t)(s / AS) & 1u);
+          tc_fence_after();
+          tc_fence_before();
+          if (elect_one()) mbar_arrive_remote(bar_peer_full + 8 * (s % AS), 0u);
+          __syncwarp();
+        }
       }
     } else if (warp == 1 || (NI == 3 && warp <= 3)) {
       // ===================== MMA issuer(s) =====================
@@ -193,6 +231,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         }
         mbar_wait(bar_w_full + 8 * wslot, (uint32_t)(s / WS) & 1u);
         mbar_wait(bar_a_full + 8 * aslot, (uint32_t)(s / AS) & 1u);
+        if (PAIR) mbar_wait(bar_peer_full + 8 * aslot, (uint32_t)(s / AS) & 1u);
         tc_fence_after();
         const uint32_t wb = sW + wslot * kStageBytes;
         const bool last_of_blk = (s + 1 == S) || (s + 1 == blk_start + FS);
@@ -203,10 +242,10 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
             for (int c = 0; c < 4; ++c) {
               const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
               const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
-              const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
-              tc_mma_f16_ts(tmem_base, a_hi, b_hi, kIdesc, accum);
-              tc_mma_f16_ts(tmem_base, a_hi + 8, b_hi, kIdesc, 1u);
-              tc_mma_f16_ts(tmem_base, a_hi, b_lo, kIdesc, 1u);
+              const uint64_t b_lo = umma_desc_sw128(wb + kLoOff + c * 32);
+              z_mma<PAIR>(tmem_base, a_hi, b_hi, kIdesc, accum);
+              z_mma<PAIR>(tmem_base, a_hi + 8, b_hi, kIdesc, 1u);
+              z_mma<PAIR>(tmem_base, a_hi, b_lo, kIdesc, 1u);
               accum = 1u;
             }
           } else if (MODE == 3) {
@@ -219,10 +258,10 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
               for (int c = c0; c < 4; c += 3) {
                 const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
                 const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
-                const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
-                tc_mma_f16_ts(d, a_hi, b_hi, kIdesc, accum);
-                tc_mma_f16_ts(d, a_hi + 8, b_hi, kIdesc, 1u);
-                tc_mma_f16_ts(d, a_hi, b_lo, kIdesc, 1u);
+                const uint64_t b_lo = umma_desc_sw128(wb + kLoOff + c * 32);
+                z_mma<PAIR>(d, a_hi, b_hi, kIdesc, accum);
+                z_mma<PAIR>(d, a_hi + 8, b_hi, kIdesc, 1u);
+                z_mma<PAIR>(d, a_hi, b_lo, kIdesc, 1u);
                 accum = 1u;
               }
             } else {
@@ -236,9 +275,9 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
                   const uint32_t d = tmem_base + (uint32_t)(ty * 128);
                   const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + c * 16);
                   const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
-                  const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+                  const uint64_t b_lo = umma_desc_sw128(wb + kLoOff + c * 32);
                   const uint32_t accum = (blk_first && pass == 0 && c < 3) ? 0u : 1u;
-                  tc_mma_f16_ts(d, pass == 1 ? a_hi + 8 : a_hi, pass == 2 ? b_lo : b_hi, kIdesc, accum);
+                  z_mma<PAIR>(d, pass == 1 ? a_hi + 8 : a_hi, pass == 2 ? b_lo : b_hi, kIdesc, accum);
                 }
               }
             }
@@ -250,19 +289,25 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
               for (int c = 0; c < 4; ++c) {
                 const uint32_t a_hi = tmem_base + kZACol + (uint32_t)(aslot * ASLOT + comp * 64 + c * 16);
                 const uint64_t b_hi = umma_desc_sw128(wb + c * 32);
-                const uint64_t b_lo = umma_desc_sw128(wb + N * 128 + c * 32);
+                const uint64_t b_lo = umma_desc_sw128(wb + kLoOff + c * 32);
                 const uint32_t d = tmem_base + (uint32_t)(comp * 128);
-                tc_mma_f16_ts(d, a_hi, b_hi, kIdesc, accum);
-                tc_mma_f16_ts(d, a_hi + 8, b_hi, kIdesc, 1u);
-                tc_mma_f16_ts(d, a_hi, b_lo, kIdesc, 1u);
+                z_mma<PAIR>(d, a_hi, b_hi, kIdesc, accum);
+                z_mma<PAIR>(d, a_hi + 8, b_hi, kIdesc, 1u);
+                z_mma<PAIR>(d, a_hi, b_lo, kIdesc, 1u);
                 accum = 1u;
               }
             }
           }
-          if (CSZ == 1) tc_commit(bar_w_empty + 8 * wslot);
-          else tc_commit_mc(bar_w_empty + 8 * wslot, kMask);
-          tc_commit(bar_a_empty + 8 * aslot);
-          if (last_of_blk) tc_commit(bar_d_full);
+          if (PAIR) {                        // one commit per barrier, multicast to both CTAs of the pair
+            tc_commit_pair(bar_w_empty + 8 * wslot, kMask);
+            tc_commit_pair(bar_a_empty + 8 * aslot, kMask);
+            if (last_of_blk) tc_commit_pair(bar_d_full, kMask);
+          } else {
+            if (CSZ == 1) tc_commit(bar_w_empty + 8 * wslot);
+            else tc_commit_mc(bar_w_empty + 8 * wslot, kMask);
+            tc_commit(bar_a_empty + 8 * aslot);
+            if (last_of_blk) tc_commit(bar_d_full);
+          }
         }
         __syncwarp();
         if (last_of_blk) { blk_start = s + 1; ++blk; }
@@ -308,7 +353,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_d_empty);
+        if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_d_empty, 0u); else mbar_arrive(bar_d_empty); }
         ++flushed;
         return;
       }
@@ -327,7 +372,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_d_empty);
+      if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_d_empty, 0u); else mbar_arrive(bar_d_empty); }
       ++flushed;
     };
 
@@ -515,7 +560,8 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   if (CSZ > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kZTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kZTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kZTmemCols) : "memory");
   }
 }
 
@@ -550,12 +596,12 @@ __global__ void zpack_kernel(const float* __restrict__ Fp, int Kp, int col0, int
   }
 }
 
-template <int MODE, int N, int CSZ>
+template <int MODE, int N, int CSZ, bool PAIR = false>
 static int launch_z(const ZParams& prm, cudaStream_t s) {
-  constexpr uint32_t kStageBytes = 2u * N * 128u;
-  constexpr int WS = kZWRingBytes / kStageBytes;
+  constexpr uint32_t kStageBytes = PAIR ? N * 128u : 2u * N * 128u;
+  constexpr int WS = (kZWRingBytes / kStageBytes > 8) ? 8 : (int)(kZWRingBytes / kStageBytes);
   const size_t smem = 1024 + (size_t)WS * kStageBytes + 512;
-  auto kern = zgemm_kernel<MODE, N, CSZ>;
+  auto kern = zgemm_kernel<MODE, N, CSZ, PAIR>;
   SE3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_mg = (prm.n_mt + CSZ - 1) / CSZ;
   cudaLaunchConfig_t cfg = {};
@@ -688,9 +734,10 @@ extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img,
   prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages
                                                      : z_env_int("SE3B200_Z_FLUSH", mode == 3 ? 24 : 8) * std::max(1, z_env_int("SE3B200_Z_FLUSH_MULT", 1)));
   const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
+  const bool pair = csz == 2 && z_env_int("SE3B200_Z_PAIR", 1) != 0;        // cta_group::2 (default) vs 2-CTA multicast of W
   cudaStream_t s = as_stream(stream);
-  if (mode == 3) return csz == 1 ? launch_z<3, 128, 1>(prm, s) : launch_z<3, 128, 2>(prm, s);
+  if (mode == 3) return csz == 1 ? launch_z<3, 128, 1>(prm, s) : pair ? launch_z<3, 128, 2, true>(prm, s) : launch_z<3, 128, 2>(prm, s);
   if (mode == 2) return csz == 1 ? launch_z<2, 128, 1>(prm, s) : launch_z<2, 128, 2>(prm, s);
-  if (N == 256) return csz == 1 ? launch_z<1, 256, 1>(prm, s) : launch_z<1, 256, 2>(prm, s);
-  return csz == 1 ? launch_z<1, 128, 1>(prm, s) : launch_z<1, 128, 2>(prm, s);
+  if (N == 256) return csz == 1 ? launch_z<1, 256, 1>(prm, s) : pair ? launch_z<1, 256, 2, true>(prm, s) : launch_z<1, 256, 2>(prm, s);
+  return csz == 1 ? launch_z<1, 128, 1>(prm, s) : pair ? launch_z<1, 128, 2, true>(prm, s) : launch_z<1, 128, 2>(prm, s);
 }
