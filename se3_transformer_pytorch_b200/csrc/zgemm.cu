@@ -96,7 +96,7 @@ __device__ __forceinline__ void z_outer16(const __half2 (&Uh)[8], const __half2 
 template <bool PAIR>
 __device__ __forceinline__ void z_mma(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   if (PAIR) tc_mma_f16_ts_pair(d, a, bdesc, idesc, accumulate);
-  else z_mma<PAIR>(d, a, bdesc, idesc, accumulate);
+  else tc_mma_f16_ts(d, a, bdesc, idesc, accumulate);
 }
 
 template <int MODE, int N, int CSZ, bool PAIR = false>
