@@ -136,8 +136,8 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
   const uint32_t bar_a_empty = bar_a_full + 8 * AS;
   const uint32_t bar_d_full = bar_a_empty + 8 * AS;
   const uint32_t bar_d_empty = bar_d_full + 8;
-  const uint32_t bar_peer_full = bar_d_empty + 8;         // [AS] (pair mode, leader): the peer's weights + Z of a stage are in place
-  const uint32_t s_tmem_slot = bar_peer_full + 8 * AS;
+  const uint32_t bar_peer_w = bar_d_empty + 8;            // [WS] (pair mode, leader): the peer's half of a weight stage is in place
+  const uint32_t s_tmem_slot = bar_peer_w + 8 * WS;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (s_tmem_slot - base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -156,12 +156,12 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
       mbar_init(bar_w_empty + 8 * s, PAIR ? NI : CSZ * NI);
     }
     for (int s = 0; s < AS; ++s) {
-      mbar_init(bar_a_full + 8 * s, 4);
+      mbar_init(bar_a_full + 8 * s, PAIR ? 8 : 4);           // pair mode: the generators of both CTAs report to the leader
       mbar_init(bar_a_empty + 8 * s, NI);
     }
     mbar_init(bar_d_full, NI);
     mbar_init(bar_d_empty, PAIR ? 16 : 8);                 // pair mode: the drain warps of both CTAs report to the leader
-    for (int s = 0; s < AS; ++s) mbar_init(bar_peer_full + 8 * s, 1);
+    for (int s = 0; s < WS; ++s) mbar_init(bar_peer_w + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -209,14 +209,13 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         __syncwarp();
       }
     } else if (PAIR && crank != 0) {
-      // ===================== pair mode, peer CTA: relay "my weights and my Z of stage s are in place" to the leader =====================
+      // ===================== pair mode, peer CTA: tell the leader when my half of a weight stage has landed =====================
+      // (the weight ring runs many stages ahead, so this relay is off the critical path; the generators of this CTA arrive on the
+      // leader's A-stage barrier themselves)
       if (warp == 1) {
         for (int s = 0; s < S; ++s) {
           mbar_wait(bar_w_full + 8 * (s % WS), (uint32_t)(s / WS) & 1u);
-          mbar_wait(bar_a_full + 8 * (s % AS), (uint32_t)(s / AS) & 1u);
-          tc_fence_after();
-          tc_fence_before();
-          if (elect_one()) mbar_arrive_remote(bar_peer_full + 8 * (s % AS), 0u);
+          if (elect_one()) mbar_arrive_remote(bar_peer_w + 8 * (s % WS), 0u);
           __syncwarp();
         }
       }
@@ -231,7 +230,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         }
         mbar_wait(bar_w_full + 8 * wslot, (uint32_t)(s / WS) & 1u);
         mbar_wait(bar_a_full + 8 * aslot, (uint32_t)(s / AS) & 1u);
-        if (PAIR) mbar_wait(bar_peer_full + 8 * aslot, (uint32_t)(s / AS) & 1u);
+        if (PAIR) mbar_wait(bar_peer_w + 8 * wslot, (uint32_t)(s / WS) & 1u);
         tc_fence_after();
         const uint32_t wb = sW + wslot * kStageBytes;
         const bool last_of_blk = (s + 1 == S) || (s + 1 == blk_start + FS);
@@ -524,7 +523,7 @@ zgemm_kernel(const __grid_constant__ ZParams prm) {
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full + 8 * aslot);
+        if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_a_full + 8 * aslot, 0u); else mbar_arrive(bar_a_full + 8 * aslot); }
 #pragma unroll
         for (int c = 0; c < NX; ++c) xv[c] = xn[c];
       }
