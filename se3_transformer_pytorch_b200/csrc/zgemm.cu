@@ -733,10 +733,12 @@ extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img,
   prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages
                                                      : z_env_int("SE3B200_Z_FLUSH", mode == 3 ? 24 : 8) * std::max(1, z_env_int("SE3B200_Z_FLUSH_MULT", 1)));
   const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
-  // cta_group::2 pair mode vs 2-CTA multicast of W.  SE3B200_Z_PAIR: bit 0 = MODE 1, bit 1 = MODE 3.  Measured (cfg2, same box):
-  // MODE 1 (N = 256, 4 A stages) 1.45-1.5 -> 1.67 PFLOP/s in pair mode (less weight traffic -> SM clock 1.45 -> 1.88 GHz);
-  // MODE 3 (two 768-cycle A stages) is latency bound through the peer's remote hand-off: 1.47 -> 0.98 PFLOP/s.  Default: MODE 1 only.
-  const int pair_bits = csz == 2 ? z_env_int("SE3B200_Z_PAIR", 1) : 0;
+  // cta_group::2 pair mode vs 2-CTA multicast of W.  SE3B200_Z_PAIR: bit 0 = MODE 1, bit 1 = MODE 3; default 0 (off).
+  // Measured (cfg2 depth-1 slice, same box, profiles/r02_pair_mode.md): in pair mode MODE 1 (N = 256, four A stages) issues 1.70
+  // instead of 1.50 PFLOP/s -- half the weight traffic per SM lets the SM clock rise from 1.45 to 1.86 GHz -- but MODE 3 (two
+  // 768-cycle A stages) cannot hide the cross-SM hand-off (remote mbarrier arrive + multicast commit per stage): 1.03 instead of
+  // 1.50 PFLOP/s; with MODE 1 alone in pair mode the power budget saved there is spent by MODE 3 and the step time is unchanged.
+  const int pair_bits = csz == 2 ? z_env_int("SE3B200_Z_PAIR", 0) : 0;
   const bool pair = (pair_bits & (mode == 3 ? 2 : 1)) != 0;
   cudaStream_t s = as_stream(stream);
   if (mode == 3) return csz == 1 ? launch_z<3, 128, 1>(prm, s) : pair ? launch_z<3, 128, 2, true>(prm, s) : launch_z<3, 128, 2>(prm, s);

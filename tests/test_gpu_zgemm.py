@@ -80,10 +80,16 @@ def _run_zgemm(mode, Co, E, seg_shapes, flush=0, seed=0, x_scale=1.0, positive=F
     (3, 256, 200, [(4, 3, 2, 0, 16), (12, 5, 3, 1, 32), (4, 7, 4, 2, 16)]),
     (3, 512, 129, [(32, 7, 6, 0, 16)]),
 ])
-def test_zgemm_matches_fp64(mode, Co, E, segs):
+@pytest.mark.parametrize('pair', [0, 3])
+def test_zgemm_matches_fp64(mode, Co, E, segs, pair, monkeypatch):
+    """pair = 3: the cta_group::2 variant (one MMA of the leader CTA drives both SMs of the cluster, each CTA streams half of the
+    weights; an option, off by default -- see se3_zgemm_fwd)."""
     from se3_transformer_pytorch_b200 import ops
     if not ops.tc_supported(DEV, Co, 1):
         pytest.skip('needs sm_100')
+    if pair and mode == 2:
+        pytest.skip('pair mode exists for modes 1 and 3')
+    monkeypatch.setenv('SE3B200_Z_PAIR', str(pair))
     for flush in (0, 1, 2, 3, 7):
         out, ref = _run_zgemm(mode, Co, E, segs, flush=flush, seed=flush)
         err = rel_err(out.cpu().numpy(), ref.cpu().numpy())
