@@ -48,9 +48,10 @@ if os.path.exists(raw):
                 to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']]) for r in rs]
         tp = [float(r[idx['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']]) for r in rs]
         z[name] = dict(launches_profiled=len(rs), dram_bytes_per_launch=sum(dram) / len(dram), tensor_pipe_pct=sum(tp) / len(tp))
-    big = max(z.items(), key=lambda kv: kv[1]['dram_bytes_per_launch'] * kv[1]['launches_profiled']) if z else None
+    conv = {k: v for k, v in z.items() if not k.startswith('zgemm_kernel<4')}       # MODE 4 is LinearSE3, timed as `linear`
+    z_all, z = z, (conv or z)
     traffic['zgemm'] = dict(source=f'profiles/{tag}_ncu_zgemm_metrics.csv (ncu --set full, cfg2 depth-1 slice, same launches as the headline)',
-                            per_variant=z,
+                            per_variant=z_all,
                             dram_bytes_per_launch=sum(v['dram_bytes_per_launch'] * v['launches_profiled'] for v in z.values()) / max(1, sum(v['launches_profiled'] for v in z.values())),
                             sm__pipe_tensor_cycles_active_pct=sum(v['tensor_pipe_pct'] * v['launches_profiled'] for v in z.values()) / max(1, sum(v['launches_profiled'] for v in z.values())))
     print('wrote', out)
