@@ -98,66 +98,67 @@ frames_kernel(const float* __restrict__ rel_pos, int64_t E, int lmax, FrameTable
 }
 
 // x'[e,i,n] = sum_q D[e][q][n] x[b(e), idx[e], i, q]   ->   X[tile][i][n][edge_local]  (128 edges per tile)
-constexpr int kRgLanes = 4;
+//
+// CTA = one edge tile x a slab of 8 input channels, 256 threads.  Gather phase: thread = (edge, channel) reads its Q
+// contiguous floats of the neighbour's feature row (a warp covers 4 edges x 8 channels: 8*Q*4 contiguous bytes per edge),
+// rotates them with the edge's Wigner block (staged in shared memory, read as a broadcast) and parks the Q results in a
+// padded shared-memory tile [channel][component][edge]; store phase: the tile goes out as whole 512-byte rows
+// X[tile][i][n][0..127].  (Round-2 first version: thread = edge with a channel loop and 4-byte stores per (channel, component):
+// 1.4 TB/s.)
+constexpr int kRgCh = 8;            // channels per CTA
+constexpr int kRgPad = 132;         // padded row of the transposing tile (conflict-free for the (edge, channel) -> [channel][n][edge] write)
 
 template <int Q>
-__global__ void __launch_bounds__(SE3_TILE_E * kRgLanes)
+__global__ void __launch_bounds__(256)
 rotgather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ D, int64_t E,
-                 int64_t mt_begin, int n, int k, int Ci, int ci_per_cta, float* __restrict__ X) {
-  extern __shared__ float Ds[];                        // [Q*Q][128]
-  const int el = threadIdx.x, lc = threadIdx.y;
+                 int64_t mt_begin, int n, int k, int Ci, float* __restrict__ X) {
+  extern __shared__ float smem_rg[];
+  float* Ds = smem_rg;                                   // [128 edges][Q*Q] (only Q > 1)
+  float* tile = smem_rg + (Q > 1 ? SE3_TILE_E * Q * Q : 0);   // [kRgCh][Q][kRgPad]
   const int64_t mt = blockIdx.x;
-  const int64_t e = (mt_begin + mt) * SE3_TILE_E + el;
-  const bool valid = e < E;
+  const int i0 = blockIdx.y * kRgCh;
+  const int64_t e0 = (mt_begin + mt) * SE3_TILE_E;
+  const int nvalid = (int)max((int64_t)0, min((int64_t)SE3_TILE_E, E - e0));
   if (Q > 1) {
-    const float* dp = D + (size_t)(valid ? e : 0) * Q * Q;
-    for (int r = lc; r < Q * Q; r += kRgLanes) Ds[r * SE3_TILE_E + el] = valid ? dp[r] : 0.f;
+    for (int t = threadIdx.x; t < nvalid * Q * Q; t += 256) Ds[t] = D[(size_t)e0 * Q * Q + t];      // contiguous block of the tile's edges
+    __syncthreads();
   }
-  const float* xrow = x;
-  if (valid) {
-    const int64_t bb = (e / k) / n;
-    xrow = x + ((size_t)(bb * n + idx[e]) * Ci) * Q;
-  }
-  const int i0 = blockIdx.y * ci_per_cta, i1 = min(Ci, i0 + ci_per_cta);
-  float* Xt = X + ((size_t)mt * Ci * Q) * SE3_TILE_E + el;
-  if (Q > 1) __syncthreads();
-  if constexpr (Q > 1 && Q <= 7) {
-    // the edge's Wigner block lives in registers for the whole channel loop (it was Q*Q shared-memory loads per channel)
-    float d[Q * Q];
-#pragma unroll
-    for (int r = 0; r < Q * Q; ++r) d[r] = Ds[r * SE3_TILE_E + el];
+  const int ch = threadIdx.x & (kRgCh - 1);              // channel inside the slab
+  const int i = i0 + ch;
 #pragma unroll 2
-    for (int i = i0 + lc; i < i1; i += kRgLanes) {
+  for (int el = threadIdx.x >> 3; el < SE3_TILE_E; el += 32) {
+    float o[Q];
+#pragma unroll
+    for (int nn = 0; nn < Q; ++nn) o[nn] = 0.f;
+    if (el < nvalid && i < Ci) {
+      const int64_t e = e0 + el;
+      const int64_t bb = (e / k) / n;
+      const float* xr = x + (((size_t)(bb * n + idx[e]) * Ci) + i) * Q;
       float xv[Q];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) xv[q] = valid ? __ldg(xrow + (size_t)i * Q + q) : 0.f;
-#pragma unroll
-      for (int nn = 0; nn < Q; ++nn) {
-        float o = 0.f;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) o = fmaf(d[q * Q + nn], xv[q], o);
-        Xt[((size_t)i * Q + nn) * SE3_TILE_E] = o;
-      }
-    }
-    return;
-  }
-#pragma unroll 4
-  for (int i = i0 + lc; i < i1; i += kRgLanes) {
-    float xv[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) xv[q] = valid ? __ldg(xrow + (size_t)i * Q + q) : 0.f;
-#pragma unroll
-    for (int nn = 0; nn < Q; ++nn) {
-      float o;
+      for (int q = 0; q < Q; ++q) xv[q] = __ldg(xr + q);
       if (Q == 1) {
-        o = xv[0];
+        o[0] = xv[0];
       } else {
-        o = 0.f;
+        const float* d = Ds + el * Q * Q;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) o = fmaf(Ds[(q * Q + nn) * SE3_TILE_E + el], xv[q], o);
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+          for (int nn = 0; nn < Q; ++nn) o[nn] = fmaf(d[q * Q + nn], xv[q], o[nn]);
       }
-      Xt[((size_t)i * Q + nn) * SE3_TILE_E] = o;
     }
+#pragma unroll
+    for (int nn = 0; nn < Q; ++nn) tile[(ch * Q + nn) * kRgPad + el] = o[nn];
+  }
+  __syncthreads();
+  // rows (channel, component) of 128 edges each: float4 stores, one warp per row at a time
+  float* Xt = X + ((size_t)mt * Ci * Q) * SE3_TILE_E;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kRgCh * Q; r += 8) {
+    const int c = r / Q;
+    if (i0 + c >= Ci) continue;
+    const float4 v = *reinterpret_cast<const float4*>(tile + r * kRgPad + lane * 4);
+    *reinterpret_cast<float4*>(Xt + ((size_t)(i0 + c) * Q + (r - c * Q)) * SE3_TILE_E + lane * 4) = v;
   }
 }
 
@@ -264,10 +265,10 @@ pow2_scale_kernel(const float* __restrict__ rowmax, int64_t rows, int target_exp
 
 template <int Q>
 static void launch_rg(dim3 grid, cudaStream_t s, const float* x, const int64_t* idx, const float* D, int64_t E, int64_t tb, int n, int k,
-                      int Ci, int cpc, float* X) {
-  const size_t smem = (size_t)Q * Q * SE3_TILE_E * sizeof(float);
+                      int Ci, float* X) {
+  const size_t smem = sizeof(float) * ((Q > 1 ? (size_t)SE3_TILE_E * Q * Q : 0) + (size_t)kRgCh * Q * kRgPad);
   cudaFuncSetAttribute(rotgather_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  rotgather_kernel<Q><<<grid, dim3(SE3_TILE_E, kRgLanes), smem, s>>>(x, idx, D, E, tb, n, k, Ci, cpc, X);
+  rotgather_kernel<Q><<<grid, 256, smem, s>>>(x, idx, D, E, tb, n, k, Ci, X);
 }
 
 }  // namespace se3
@@ -298,18 +299,15 @@ extern "C" int se3_rotgather_fwd(const float* x, const int64_t* idx, const float
   const int64_t E = (int64_t)b * n * k;
   const int64_t n_all = ceil_div(E, SE3_TILE_E);
   SE3_REQUIRE(tile_begin >= 0 && tile_count > 0 && tile_begin + tile_count <= n_all, "se3_rotgather_fwd: tile range out of bounds");
-  int slabs = (int)std::min<int64_t>(std::max(1, Ci / 16), std::max<int64_t>(1, (148 * 2 + tile_count - 1) / tile_count));
-  const int cpc = (int)ceil_div(Ci, slabs);
-  slabs = (int)ceil_div(Ci, cpc);
-  dim3 grid((unsigned)tile_count, (unsigned)slabs);
+  dim3 grid((unsigned)tile_count, (unsigned)ceil_div(Ci, kRgCh));
   cudaStream_t st = as_stream(stream);
   switch (Q) {
-    case 1: launch_rg<1>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
-    case 3: launch_rg<3>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
-    case 5: launch_rg<5>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
-    case 7: launch_rg<7>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
-    case 9: launch_rg<9>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
-    default: launch_rg<11>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, cpc, X); break;
+    case 1: launch_rg<1>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
+    case 3: launch_rg<3>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
+    case 5: launch_rg<5>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
+    case 7: launch_rg<7>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
+    case 9: launch_rg<9>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
+    default: launch_rg<11>(grid, st, x, idx, D, E, tile_begin, n, k, Ci, X); break;
   }
   SE3_LAUNCH_OK();
   return SE3_OK;
