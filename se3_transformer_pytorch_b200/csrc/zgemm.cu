@@ -732,7 +732,8 @@ extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img,
   // accumulators): rel. error 4e-6 against float64 for all-positive operands at K = 65536 (2.5e-4 if never drained)
   prm.flush_stages = std::max(1, flush_stages > 0 ? flush_stages
                                                      : z_env_int("SE3B200_Z_FLUSH", mode == 3 ? 24 : 8) * std::max(1, z_env_int("SE3B200_Z_FLUSH_MULT", 1)));
-  const int csz = z_env_int("SE3B200_Z_CLUSTER", 2) == 1 ? 1 : 2;
+  const int csz_env = z_env_int("SE3B200_Z_CLUSTER", 2);
+  const int csz = csz_env == 1 ? 1 : (csz_env == 4 && prm.n_mt % 4 == 0 && mode != 2) ? 4 : 2;
   // cta_group::2 pair mode vs 2-CTA multicast of W.  SE3B200_Z_PAIR: bit 0 = MODE 1, bit 1 = MODE 3; default 0 (off).
   // Measured (cfg2 depth-1 slice, same box, profiles/r02_pair_mode.md): in pair mode MODE 1 (N = 256, four A stages) issues 1.70
   // instead of 1.50 PFLOP/s -- half the weight traffic per SM lets the SM clock rise from 1.45 to 1.86 GHz -- but MODE 3 (two
@@ -741,6 +742,10 @@ extern "C" int se3_zgemm_fwd(const se3_zseg* segs, int n_seg, const void* w_img,
   const int pair_bits = csz == 2 ? z_env_int("SE3B200_Z_PAIR", 0) : 0;
   const bool pair = (pair_bits & (mode == 3 ? 2 : 1)) != 0;
   cudaStream_t s = as_stream(stream);
+  if (csz == 4) {                            // 4-CTA multicast of W (experiment: a quarter of the L2 reads per SM)
+    if (mode == 3) return launch_z<3, 128, 4>(prm, s);
+    return N == 256 ? launch_z<1, 256, 4>(prm, s) : launch_z<1, 128, 4>(prm, s);
+  }
   if (mode == 3) return csz == 1 ? launch_z<3, 128, 1>(prm, s) : pair ? launch_z<3, 128, 2, true>(prm, s) : launch_z<3, 128, 2>(prm, s);
   if (mode == 2) return csz == 1 ? launch_z<2, 128, 1>(prm, s) : launch_z<2, 128, 2>(prm, s);
   if (N == 256) return csz == 1 ? launch_z<1, 256, 1>(prm, s) : pair ? launch_z<1, 256, 2, true>(prm, s) : launch_z<1, 256, 2>(prm, s);
