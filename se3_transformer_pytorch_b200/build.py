@@ -31,9 +31,9 @@ def _nvcc():
 def _digest():
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(os.path.dirname(PKG), 'include', 'se3b200.h')]
-    for f in files:
-        with open(f, 'rb') as fh:
-            h.update(f.encode() + b'\0' + fh.read())
+    for f in files:                                   # names relative to the package: the stamp must survive a move of the tree
+        with open(f, 'rb') as fh:                     # (the GPU box runs a copy of the repository under another path)
+            h.update(os.path.basename(f).encode() + b'\0' + fh.read())
     h.update(' '.join(NVCC_FLAGS + EXTRA_DEFS).encode())
     return h.hexdigest()
 
@@ -46,11 +46,25 @@ def is_current():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library next to this file."""
+    """Compile every .cu under csrc/ into one shared library next to this file.  Safe to call from several processes at once
+    (one rank per GPU under torchrun): an exclusive file lock serialises them, the library is linked under a temporary name and
+    renamed into place, so a concurrent loader sees either the old or the new file, never a partial one."""
     if not force and is_current():
         return LIB
     if not force and TAG and 'SE3B200_NVCC_DEFS' not in os.environ and os.path.exists(LIB):
         return LIB                                   # a tagged experiment variant built elsewhere: load it as it is
+    import fcntl
+    with open(os.path.join(PKG, f'.libse3b200{TAG}.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():           # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + EXTRA_DEFS
     objs = []
@@ -75,9 +89,12 @@ def build(force=False, verbose=False):
             print(f'nvcc failed on {src}', file=sys.stderr)
     if failed:
         raise RuntimeError('libse3b200 build failed')
-    subprocess.check_call([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB, *objs])
-    with open(STAMP, 'w') as f:
+    tmp = f'{LIB}.{os.getpid()}.tmp'
+    subprocess.check_call([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp, *objs])
+    os.replace(tmp, LIB)
+    with open(STAMP + '.tmp', 'w') as f:
         f.write(_digest())
+    os.replace(STAMP + '.tmp', STAMP)
     return LIB
 
 
