@@ -35,6 +35,26 @@ def test_library_exports_every_declared_symbol():
     assert ops.lib().se3_abi_version() == 1
 
 
+def test_build_stamp_survives_a_move_of_the_tree(tmp_path):
+    """The GPU box runs a copy of the repository under another path and must load the library that was built here: the
+    staleness digest may depend on file names and contents only (it once hashed absolute paths, so every box rebuilt and
+    the ranks of a torchrun launch raced on the link step)."""
+    import importlib.util
+    import shutil
+    import se3_transformer_pytorch_b200.build as B
+    root = os.path.dirname(B.PKG)
+    dst = tmp_path / 'moved'
+    shutil.copytree(os.path.join(B.PKG, 'csrc'), dst / 'pkg' / 'csrc')
+    shutil.copytree(os.path.join(root, 'include'), dst / 'include')
+    shutil.copy(os.path.join(B.PKG, 'build.py'), dst / 'pkg' / 'build.py')
+    spec = importlib.util.spec_from_file_location('moved_build', dst / 'pkg' / 'build.py')
+    M = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(M)
+    assert M.PKG != B.PKG and M._digest() == B._digest()
+    B.build()
+    assert B.is_current()                  # the in-tree library matches the sources
+
+
 def test_constructor_assertions_match_reference():
     from se3_transformer_pytorch_b200 import SE3Transformer
     with pytest.raises(AssertionError):          # reference S:1048
