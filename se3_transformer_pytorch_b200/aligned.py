@@ -91,9 +91,9 @@ def _samples(l, device):
     if key not in _SAMPLES:
         g = torch.Generator().manual_seed(1000 + l)
         xs = torch.randn(2 * l + 3, 3, generator=g, dtype=torch.float64)
-        xs = (xs / xs.norm(dim=-1, keepdim=True)).to(device)
-        pin = torch.linalg.pinv(real_sh64(xs, l)[l])          # [M, S]
-        _SAMPLES[key] = (xs, pin)
+        xs = xs / xs.norm(dim=-1, keepdim=True)
+        pin = torch.linalg.pinv(real_sh64(xs, l)[l])          # [M, S]; tiny, on the host (no device SVD launches)
+        _SAMPLES[key] = (xs.to(device), pin.to(device))
     return _SAMPLES[key]
 
 
