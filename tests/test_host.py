@@ -339,3 +339,33 @@ def test_lowrank_conv_dispatch_on_cpu_emulation(monkeypatch, frame):
         got = out[str(do)].reshape(E, C, 2 * do + 1).numpy()
         worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
     assert worst < 2e-5, worst
+
+
+def _run_bench(extra, env=None):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **(env or {}))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', 'cfg1', '--steps', '1',
+                        '--warmup', '0', '--cpu-flops', '1e8'] + extra, capture_output=True, text=True, timeout=300, env=e, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith('{')]
+    return [json.loads(ln) for ln in lines]
+
+
+def test_reference_arm_prints_the_contract_line_on_cpu():
+    """bench.py --impl reference: the oracle on the host cores, no GPU needed; one JSON line with the contract's keys."""
+    (line,) = _run_bench([])
+    assert line['impl'] == 'reference' and line['metric'] == 'point-clouds/sec fwd' and line['unit'] == 'clouds/s'
+    assert line['higher_is_better'] is True and line['n_gpus'] == 1 and line['steps'] == 1 and line['gpu_launches'] == 0
+    assert line['value'] > 0 and abs(line['e2e']['value'] - line['value']) < 1e-12
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and 'ConvSE3' in cb['sample'] and cb['value'] == line['value']
+    assert line['config']['workload'] == 'cfg1'
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work."""
+    assert _run_bench(['--gpus', '2'], env={'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}) == []
