@@ -369,3 +369,27 @@ def test_reference_arm_prints_the_contract_line_on_cpu():
 def test_reference_arm_other_ranks_exit_quietly():
     """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work."""
     assert _run_bench(['--gpus', '2'], env={'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}) == []
+
+
+def test_concurrent_builds_do_not_race(tmp_path):
+    """One process per GPU: every rank may find the library missing at the same moment.  Three processes build a moved copy of
+    the sources at once; the file lock lets one of them compile, the others wait and load the finished library (a rank once
+    dlopen'ed a half-linked file: 'invalid ELF header')."""
+    import shutil
+    import subprocess
+    import sys
+    import se3_transformer_pytorch_b200.build as B
+    root = os.path.dirname(B.PKG)
+    dst = tmp_path / 'moved'
+    shutil.copytree(os.path.join(B.PKG, 'csrc'), dst / 'pkg' / 'csrc')
+    shutil.copytree(os.path.join(root, 'include'), dst / 'include')
+    shutil.copy(os.path.join(B.PKG, 'build.py'), dst / 'pkg' / 'build.py')
+    code = ('import importlib.util, ctypes, sys\n'
+            f'spec = importlib.util.spec_from_file_location("moved_build", r"{dst / "pkg" / "build.py"}")\n'
+            'M = importlib.util.module_from_spec(spec); spec.loader.exec_module(M)\n'
+            'h = ctypes.CDLL(M.build()); assert h.se3_abi_version() > 0; print("loaded")\n')
+    procs = [subprocess.Popen([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in range(3)]
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0 and 'loaded' in out, err[-2000:]
+    assert not [f for f in os.listdir(dst / 'pkg') if f.endswith('.tmp')]
